@@ -1,0 +1,116 @@
+/* libmonoflex_b200.so — C ABI of the B200-native MonoFlex hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers and sizes; no torch / ATen types. Every buffer (inputs, outputs, workspaces) is allocated
+ *     and owned by the caller; the library never calls cudaMalloc on the hot path and keeps no global device state.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream.
+ *   - return value 0 = success, negative = error; mf_last_error() returns the thread-local message
+ *     (the Python host raises RuntimeError, mirroring AT_ASSERTM/AT_ERROR -> RuntimeError in the reference,
+ *     /root/reference/model/backbone/DCNv2/src/dcn_v2.h:25-45).
+ *   - internal activation layout is NHWC fp16 ("pixel rows"): `*_ld` is the element stride between consecutive pixels,
+ *     so a tensor may be a channel slice of a wider buffer (used to write Root/concat inputs in place).
+ *
+ * Each entry point names the reference interface it replaces.
+ */
+#ifndef MONOFLEX_B200_H
+#define MONOFLEX_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ------------------------------------------------------------------------------------------ */
+const char* mf_last_error(void);
+int mf_version(void);
+/* 0 = tcgen05 tensor-core implicit GEMM (default, the product), 1 = CUDA-core cross-check kernels (diagnostics). */
+int mf_set_conv_impl(int impl);
+/* N tile (16/32/64/128) the conv kernels use for `cout`; packed weights / scale / shift are padded to a multiple. */
+int mf_conv_block_n(int cout);
+
+/* ---- activation codes / output modes ------------------------------------------------------------------------ */
+#define MF_ACT_NONE 0
+#define MF_ACT_RELU 1
+#define MF_ACT_LEAKY 2   /* leaky_relu 0.01 (InPlaceABN, detector_predictor.py:50,74) */
+#define MF_ACT_OFFMASK 3 /* channels >= 18 -> sigmoid (DCN.forward dcn_v2.py:119-122) */
+#define MF_OUT_F16_NHWC 0
+#define MF_OUT_F32_NHWC 1
+#define MF_OUT_F32_NCHW 2
+
+/* OIHW fp32 conv weight -> [n_pad, k_pad] fp16, k = (ky*kw + kx)*cin_pad + c, zero padded
+ * (replaces the cuDNN/THC weight layouts behind nn.Conv2d and _ext, dla_dcn.py:70-98, dcn_v2.py:69-73). */
+int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
+                        void* out_f16, void* stream);
+
+/* Conv2d + per-channel affine (folded BatchNorm / bias) + optional residual + activation as one tcgen05 implicit GEMM.
+ * Replaces nn.Conv2d -> BatchNorm2d -> (+=residual) -> ReLU chains: dla_dcn.py:84-98 (BasicBlock), :195-203 (Root),
+ * :268-322 (base layers), DCN.conv_offset_mask dcn_v2.py:106-122 (MF_ACT_OFFMASK, MF_OUT_F32_NHWC, y_ld = 32),
+ * head 3x3 + InPlaceABN detector_predictor.py:47-75 (MF_ACT_LEAKY), head 1x1 :52,:83 (MF_OUT_F32_NCHW).
+ * y[m, n] = act(scale[n] * sum_k x[...] w[n, k] + shift[n] (+ res[m, n])); scale/shift have n_pad entries. */
+int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w_packed, int n_pad, int k_pad,
+                       int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift,
+                       const void* res, int res_ld, int act, int out_mode, void* y, int y_ld, void* stream);
+
+/* Fused DCNv2 (3x3, stride 1, pad 1, dilation 1, deformable_groups 1): bilinear gather of the modulated columns straight
+ * into the MMA operand tile, contraction with the packed weights, affine (+bias, BN) and activation epilogue.
+ * Replaces _ext.dcn_v2_forward + BatchNorm2d + ReLU of DeformConv (dla_dcn.py:384-396; src/cuda/dcn_v2_cuda.cu:42-172,
+ * src/cuda/dcn_v2_im2col_cuda.cu:125-195) without the [B, 9C, HW] columns buffer.
+ * offmask: [B*H*W, om_ld] fp32 rows = 18 offsets (dy,dx per tap) + 9 sigmoid-ed masks. */
+int mf_dcn_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const float* offmask, int om_ld,
+                    const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
+                    int out_mode, void* y, int y_ld, void* stream);
+
+/* ---- layout / HBM-bound kernels ----------------------------------------------------------------------------- */
+/* images [B,C<=8,H,W] fp32 NCHW (engine/trainer.py:106, engine/inference.py:29) -> NHWC fp16 with 8 channels */
+int mf_pack_image(const float* x_nchw, void* y_nhwc8, int B, int C, int H, int W, void* stream);
+int mf_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int C, int HW, int y_ld, void* stream);
+int mf_nhwc_f16_to_nchw_f32(const void* x, float* y, int B, int C, int HW, int x_ld, void* stream);
+/* offset [B,18,H,W] + mask [B,9,H,W] (reference _ext layout) -> [B*HW, 32] fp32 rows */
+int mf_pack_offmask(const float* offset, const float* mask, float* y, int B, int HW, void* stream);
+/* nn.MaxPool2d(2) of Tree.downsample (dla_dcn.py:238) */
+int mf_maxpool2_nhwc_f16(const void* x, void* y, int B, int H, int W, int C, int x_ld, int y_ld, void* stream);
+/* depthwise ConvTranspose2d(k=2f, stride f, pad f/2) + skip add (IDAUp.forward dla_dcn.py:419-425).
+ * w_taps: fp32 [k*k, C] */
+int mf_upsample_add_nhwc_f16(const void* x, const float* w_taps, const void* skip, void* y, int B, int Hi, int Wi, int C,
+                             int f, int x_ld, int skip_ld, int y_ld, void* stream);
+/* edge fusion (detector_predictor.py:137-158): grid_sample of two 256-ch slices at the border pixels into two
+ * replicate-padded Conv1d inputs [B, K+2, 256]; final Conv1d(256->n_out,k=1) + indexed add into an NCHW fp32 map. */
+int mf_edge_gather(const void* feat, int feat_ld, int ch_a, int ch_b, const long long* edge_idx, void* ea, void* eb, int B,
+                   int H, int W, int K, int out_w, int out_h, void* stream);
+int mf_edge_head_add(const void* t, const float* w, const float* bias, int n_out, const long long* edge_idx,
+                     const long long* edge_len, float* out, int out_ctot, int out_ch0, int B, int K, int H, int W,
+                     void* stream);
+/* sigmoid_hm (model/layers/utils.py:39-43), in place */
+int mf_sigmoid_clamp(float* x, long long n, void* stream);
+/* FocalLoss.forward (model/layers/focal_loss.py:35-55): out2[0] = loss sum, out2[1] = num_pos */
+int mf_focal_loss_forward(const float* pred, const float* target, long long n, float* out2, void* stream);
+
+/* nms_hm alone (model/layers/utils.py:45-58): out = heat * (maxpool3x3(heat) == heat), planes = B*C */
+int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream);
+
+/* nms_hm + select_topk + select_point_of_interest + PostProcessor decode (model/layers/utils.py:45-145,
+ * model/head/detector_infer.py:77-237, model/anno_encoder.py:69-295) for a whole batch.
+ * heat [B,C,H,W] fp32 (apply_sigmoid=1: raw logits), reg [B,R=50,H,W] fp32, calib [B,6] = f_u,f_v,c_u,c_v,b_x,b_y,
+ * pad [B,2], size [B,2] = (W,H) of the padded image, dim_mean [C,3]. Workspaces ws_score/ws_idx: [B*C*K].
+ * Outputs: scores/clses/ys/xs [B,K] fp32, inds [B,K] int64, pois [B,K,R], result [B,K,14], count [B] = #(score>=thresh). */
+int mf_decode_detections(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
+                         const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
+                         float* ws_score, int* ws_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
+                         float* pois, float* result, int* count, void* stream);
+
+/* ---- boundary B: the reference's native operator ABI (_ext, src/vision.cpp:4-9, src/dcn_v2.h:9-59) ------------ */
+/* at::Tensor dcn_v2_forward(input, weight, bias, offset, mask, kh,kw,sh,sw,ph,pw,dh,dw,deformable_group): fp32 NCHW,
+ * exact fp32 arithmetic (passes testcuda.py:check_zero_offset at 1e-10). y is caller-allocated [B,Cout,Ho,Wo]. */
+int mf_dcn_v2_forward(const float* x, const float* w, const float* bias, const float* offset, const float* mask, float* y,
+                      int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                      int dw, int dg, void* workspace, size_t ws_bytes, void* stream);
+/* dcn_v2_backward (src/dcn_v2.h:48-59): training path, not built yet -> returns -2 */
+int mf_dcn_v2_backward(void);
+/* dcn_v2_psroi_pooling_forward/backward (src/dcn_v2.h:94-153): never instantiated by MonoFlex -> stubs returning -2 */
+int mf_dcn_v2_psroi_pooling_forward(void);
+int mf_dcn_v2_psroi_pooling_backward(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOFLEX_B200_H */

@@ -1,0 +1,74 @@
+"""ctypes binding of libmonoflex_b200.so (include/monoflex_b200.h). There is NO fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised (the reference's AT_ASSERTM/AT_ERROR also surface as RuntimeError,
+/root/reference/model/backbone/DCNv2/src/dcn_v2.h:25-45)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmonoflex_b200.so")
+_lib = None
+
+_P, _I, _F, _LL, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
+
+# name -> argtypes (restype int unless stated). Mirrors include/monoflex_b200.h one to one.
+SIGNATURES = {
+    "mf_version": [],
+    "mf_set_conv_impl": [_I],
+    "mf_conv_block_n": [_I],
+    "mf_pack_conv_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mf_conv2d_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
+    "mf_dcn_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P],
+    "mf_pack_image": [_P, _P, _I, _I, _I, _I, _P],
+    "mf_nchw_f32_to_nhwc_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "mf_nhwc_f16_to_nchw_f32": [_P, _P, _I, _I, _I, _I, _P],
+    "mf_pack_offmask": [_P, _P, _P, _I, _I, _P],
+    "mf_maxpool2_nhwc_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mf_upsample_add_nhwc_f16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mf_edge_gather": [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mf_edge_head_add": [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mf_sigmoid_clamp": [_P, _LL, _P],
+    "mf_focal_loss_forward": [_P, _P, _LL, _P, _P],
+    "mf_nms_hm": [_P, _P, _I, _I, _I, _P],
+    "mf_decode_detections": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                             _P, _P],
+    "mf_dcn_v2_forward": [_P, _P, _P, _P, _P, _P] + [_I] * 14 + [_P, _SZ, _P],
+    "mf_dcn_v2_backward": [],
+    "mf_dcn_v2_psroi_pooling_forward": [],
+    "mf_dcn_v2_psroi_pooling_backward": [],
+}
+
+
+def load():
+    """dlopen the in-tree library (built by __graft_entry__.build()); raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("monoflex_b200: %s not built - run `python __graft_entry__.py` (nvcc, sm_100a). "
+                               "There is no CPU or PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.mf_last_error.restype = ctypes.c_char_p
+        lib.mf_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = _I
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.mf_last_error().decode()))
+    return rc
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,235 @@
+// C ABI of libmonoflex_b200.so (declared in include/monoflex_b200.h). Plain pointers and sizes only; the caller owns
+// every buffer (torch's caching allocator in the Python host), kernels run on the caller's stream, no global state except
+// the thread-local last-error string and the debug conv-implementation switch.
+#include "mf_common.cuh"
+#include "mf_kernels.h"
+#include "mf_launch.h"
+#include "../../include/monoflex_b200.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace mf {
+
+static thread_local char g_err[512] = "";
+static int g_conv_impl = 0;  // 0 = tcgen05 implicit GEMM, 1 = CUDA-core cross-check
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+
+// ---------------------------------------------------------------- weight repack: OIHW fp32 -> [n_pad, k_pad] fp16, k = tap*cin_pad + c
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int cin_pad, int n_pad,
+                                        int k_pad, __half* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n_pad) * k_pad) return;
+  const int k = static_cast<int>(i % k_pad), n = static_cast<int>(i / k_pad);
+  const int tap = k / cin_pad, c = k - tap * cin_pad;
+  float v = 0.f;
+  if (n < Cout && tap < taps && c < Cin) v = w[(static_cast<long long>(n) * Cin + c) * taps + tap];
+  out[i] = __float2half_rn(v);
+}
+int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
+                            __half* out, cudaStream_t st) {
+  if (cin_pad < Cin || k_pad < kh * kw * cin_pad || n_pad < Cout) { set_error("pack_conv_weight: bad padding"); return -1; }
+  const long long n = static_cast<long long>(n_pad) * k_pad;
+  pack_conv_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(w, Cout, Cin, kh * kw, cin_pad, n_pad,
+                                                                                 k_pad, out);
+  return check_cuda(cudaGetLastError(), "pack_conv_weight");
+}
+
+// ---------------------------------------------------------------- boundary B: exact-fp32 DCNv2 forward, reference _ext layout
+// (NCHW fp32 in/out; src/dcn_v2.h:9-23, semantics of src/cuda/dcn_v2_im2col_cuda.cu:125-195 + dcn_v2_cuda.cu:126-163).
+// One thread per output element; no columns buffer. This is the operator-ABI compatibility path (testcuda.py KATs); the
+// detector's hot path uses the fused NHWC fp16 tensor-core kernel instead.
+__global__ void dcn_v2_forward_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                          const float* __restrict__ bias, const float* __restrict__ off,
+                                          const float* __restrict__ mask, float* __restrict__ y, int B, int Cin, int H,
+                                          int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                                          int dg, int Ho, int Wo) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Cout * Ho * Wo;
+  if (i >= total) return;
+  const int ox = static_cast<int>(i % Wo);
+  long long t = i / Wo;
+  const int oy = static_cast<int>(t % Ho);
+  t /= Ho;
+  const int o = static_cast<int>(t % Cout);
+  const int b = static_cast<int>(t / Cout);
+  const int taps = kh * kw, cpg = Cin / dg;
+  const long long HoWo = static_cast<long long>(Ho) * Wo, pix = static_cast<long long>(oy) * Wo + ox;
+  float acc = bias[o];
+  for (int g = 0; g < dg; ++g) {
+    const float* offp = off + (static_cast<long long>(b) * dg + g) * 2 * taps * HoWo;
+    const float* mp = mask + (static_cast<long long>(b) * dg + g) * taps * HoWo;
+    for (int tap = 0; tap < taps; ++tap) {
+      const int ki = tap / kw, kj = tap - ki * kw;
+      const float h_im = static_cast<float>(oy * sh - ph + ki * dh) + offp[(2 * tap) * HoWo + pix];
+      const float w_im = static_cast<float>(ox * sw - pw + kj * dw) + offp[(2 * tap + 1) * HoWo + pix];
+      if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(H) && w_im < static_cast<float>(W))) continue;
+      const float mk = mp[tap * HoWo + pix];
+      const float hlf = floorf(h_im), wlf = floorf(w_im);
+      const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
+      const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf), hi = hl + 1, wi = wl + 1;
+      const bool tp = hl >= 0, bt = hi <= H - 1, lf = wl >= 0, rt = wi <= W - 1;
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        const float* xp = x + (static_cast<long long>(b) * Cin + c) * H * W;
+        const float v1 = (tp && lf) ? xp[hl * W + wl] : 0.f;
+        const float v2 = (tp && rt) ? xp[hl * W + wi] : 0.f;
+        const float v3 = (bt && lf) ? xp[hi * W + wl] : 0.f;
+        const float v4 = (bt && rt) ? xp[hi * W + wi] : 0.f;
+        const float val = (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4) * mk;
+        acc += val * w[(static_cast<long long>(o) * Cin + c) * taps + tap];
+      }
+    }
+  }
+  y[i] = acc;
+}
+int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias, const float* off, const float* mask,
+                              float* y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
+                              int pw, int dh, int dw, int dg, cudaStream_t st) {
+  const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+  const int Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+  const long long n = static_cast<long long>(B) * Cout * Ho * Wo;
+  dcn_v2_forward_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, w, bias, off, mask, y, B, Cin, H, W,
+                                                                                   Cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                                                                                   dg, Ho, Wo);
+  return check_cuda(cudaGetLastError(), "dcn_v2_forward_f32");
+}
+
+static int run_gemm(const IgemmParams& p, const void* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
+  if (g_conv_impl == 1) return launch_simt_gemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
+  return launch_igemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
+}
+
+}  // namespace mf
+
+using namespace mf;
+#define MF_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* mf_last_error(void) { return g_err; }
+int mf_version(void) { return 100; }
+int mf_set_conv_impl(int impl) {
+  if (impl != 0 && impl != 1) { set_error("mf_set_conv_impl: impl must be 0 or 1"); return -1; }
+  g_conv_impl = impl;
+  return 0;
+}
+int mf_conv_block_n(int cout) { return igemm_block_n(cout); }
+
+int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
+                        void* out_f16, void* stream) {
+  return launch_pack_conv_weight(w_oihw, Cout, Cin, kh, kw, cin_pad, n_pad, k_pad, static_cast<__half*>(out_f16),
+                                 MF_STREAM(stream));
+}
+
+int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w_packed, int n_pad, int k_pad,
+                       int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift,
+                       const void* res, int res_ld, int act, int out_mode, void* y, int y_ld, void* stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __half*>(x); p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - kh) / stride + 1;
+  p.Wo = (W + 2 * pad - kw) / stride + 1;
+  p.M = B * p.Ho * p.Wo;
+  p.K_real = kh * kw * Cin;
+  p.nkb = (p.K_real + 63) / 64;
+  p.Cout = Cout; p.scale = scale; p.shift = shift;
+  p.res = static_cast<const __half*>(res); p.res_ld = res_ld; p.act = act; p.out_mode = out_mode; p.y = y; p.y_ld = y_ld;
+  if (p.Ho <= 0 || p.Wo <= 0 || Cout <= 0) { set_error("mf_conv2d_nhwc_f16: empty output"); return -1; }
+  return run_gemm(p, w_packed, n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
+}
+
+int mf_dcn_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const float* offmask, int om_ld,
+                    const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
+                    int out_mode, void* y, int y_ld, void* stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __half*>(x); p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.kh = 3; p.kw = 3; p.stride = 1; p.pad = 1; p.Ho = H; p.Wo = W; p.M = B * H * W;
+  p.K_real = 9 * Cin; p.nkb = (p.K_real + 63) / 64;
+  p.offmask = offmask; p.om_ld = om_ld;
+  p.Cout = Cout; p.scale = scale; p.shift = shift; p.act = act; p.out_mode = out_mode; p.y = y; p.y_ld = y_ld;
+  if (om_ld < 27) { set_error("mf_dcn_nhwc_f16: om_ld < 27"); return -1; }
+  return run_gemm(p, w_packed, n_pad, k_pad, MODE_DCN, MF_STREAM(stream));
+}
+
+int mf_pack_image(const float* x_nchw, void* y_nhwc8, int B, int C, int H, int W, void* stream) {
+  return launch_pack_image(x_nchw, static_cast<__half*>(y_nhwc8), B, C, H, W, MF_STREAM(stream));
+}
+int mf_nchw_f32_to_nhwc_f16(const float* x, void* y, int B, int C, int HW, int y_ld, void* stream) {
+  return launch_nchw_to_nhwc(x, static_cast<__half*>(y), B, C, HW, y_ld, MF_STREAM(stream));
+}
+int mf_nhwc_f16_to_nchw_f32(const void* x, float* y, int B, int C, int HW, int x_ld, void* stream) {
+  return launch_nhwc_to_nchw(static_cast<const __half*>(x), y, B, C, HW, x_ld, MF_STREAM(stream));
+}
+int mf_pack_offmask(const float* offset, const float* mask, float* y, int B, int HW, void* stream) {
+  return launch_pack_offmask(offset, mask, y, B, HW, MF_STREAM(stream));
+}
+int mf_maxpool2_nhwc_f16(const void* x, void* y, int B, int H, int W, int C, int x_ld, int y_ld, void* stream) {
+  return launch_maxpool2(static_cast<const __half*>(x), static_cast<__half*>(y), B, H, W, C, x_ld, y_ld, MF_STREAM(stream));
+}
+int mf_upsample_add_nhwc_f16(const void* x, const float* w_taps, const void* skip, void* y, int B, int Hi, int Wi, int C,
+                             int f, int x_ld, int skip_ld, int y_ld, void* stream) {
+  return launch_upsample_add(static_cast<const __half*>(x), w_taps, static_cast<const __half*>(skip),
+                             static_cast<__half*>(y), B, Hi, Wi, C, f, x_ld, skip_ld, y_ld, MF_STREAM(stream));
+}
+int mf_edge_gather(const void* feat, int feat_ld, int ch_a, int ch_b, const long long* edge_idx, void* ea, void* eb, int B,
+                   int H, int W, int K, int out_w, int out_h, void* stream) {
+  return launch_edge_gather(static_cast<const __half*>(feat), feat_ld, ch_a, ch_b, edge_idx, static_cast<__half*>(ea),
+                            static_cast<__half*>(eb), B, H, W, K, out_w, out_h, MF_STREAM(stream));
+}
+int mf_edge_head_add(const void* t, const float* w, const float* bias, int n_out, const long long* edge_idx,
+                     const long long* edge_len, float* out, int out_ctot, int out_ch0, int B, int K, int H, int W,
+                     void* stream) {
+  return launch_edge_head_add(static_cast<const __half*>(t), w, bias, n_out, edge_idx, edge_len, out, out_ctot, out_ch0, B,
+                              K, H, W, MF_STREAM(stream));
+}
+int mf_sigmoid_clamp(float* x, long long n, void* stream) { return launch_sigmoid_clamp(x, n, MF_STREAM(stream)); }
+int mf_focal_loss_forward(const float* pred, const float* target, long long n, float* out2, void* stream) {
+  return launch_focal_loss(pred, target, n, out2, MF_STREAM(stream));
+}
+int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream) {
+  return launch_nms_hm(heat, out, planes, H, W, MF_STREAM(stream));
+}
+int mf_decode_detections(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
+                         const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
+                         float* ws_score, int* ws_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
+                         float* pois, float* result, int* count, void* stream) {
+  return launch_decode(heat, reg, calib, pad, size, dim_mean, B, C, H, W, R, K, thresh, apply_sigmoid, ws_score, ws_idx,
+                       scores, inds, clses, ys, xs, pois, result, count, MF_STREAM(stream));
+}
+
+int mf_dcn_v2_forward(const float* x, const float* w, const float* bias, const float* offset, const float* mask, float* y,
+                      int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                      int dw, int dg, void* workspace, size_t ws_bytes, void* stream) {
+  (void)workspace; (void)ws_bytes;
+  if (dg < 1 || Cin % dg != 0) { set_error("mf_dcn_v2_forward: channels %d not divisible by deformable_group %d", Cin, dg); return -1; }
+  return launch_dcn_v2_forward_f32(x, w, bias, offset, mask, y, B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg,
+                                   MF_STREAM(stream));
+}
+int mf_dcn_v2_backward(void) {
+  set_error("mf_dcn_v2_backward: not built yet (training path is a later SURVEY section-8 row)");
+  return -2;
+}
+int mf_dcn_v2_psroi_pooling_forward(void) {
+  set_error("dcn_v2_psroi_pooling_forward: not built (dead code for MonoFlex, SURVEY 2.2 K6)");
+  return -2;
+}
+int mf_dcn_v2_psroi_pooling_backward(void) {
+  set_error("dcn_v2_psroi_pooling_backward: not built (dead code for MonoFlex, SURVEY 2.2 K6)");
+  return -2;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Internal launcher declarations shared by the .cu files of libmonoflex_b200.so (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace mf {
+
+enum { MODE_CONV = 0, MODE_DCN = 1 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFMASK = 3 };
+enum { OUT_F16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
+
+struct IgemmParams {
+  // A operand: NHWC fp16 activations, `x_ld` elements between consecutive pixels (>= Cin: channel-slice views)
+  const __half* x;
+  int x_ld;
+  int B, H, W, Cin;
+  int Ho, Wo, kh, kw, stride, pad;
+  int M;        // B*Ho*Wo
+  int K_real;   // kh*kw*Cin
+  int nkb;      // ceil(K_real / 64)
+  // DCN: per output pixel 18 offsets (dy,dx per tap) + 9 masks (already sigmoid-ed), fp32, row stride om_ld
+  const float* offmask;
+  int om_ld;
+  // epilogue: y = act(acc*scale[n] + shift[n] (+ res[m,n]))
+  int Cout;
+  const float* scale;
+  const float* shift;
+  const __half* res;
+  int res_ld;
+  int act;
+  int out_mode;
+  void* y;
+  int y_ld;
+};
+
+int igemm_block_n(int cout);
+int launch_igemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
+int launch_simt_gemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
+
+}  // namespace mf

@@ -1,0 +1,31 @@
+// Launcher prototypes of the HBM-bound kernels (internal; the public C ABI is include/monoflex_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+namespace mf {
+int launch_pack_image(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st);
+int launch_nchw_to_nhwc(const float* x, __half* y, int B, int C, int HW, int y_ld, cudaStream_t st);
+int launch_nhwc_to_nchw(const __half* x, float* y, int B, int C, int HW, int x_ld, cudaStream_t st);
+int launch_pack_offmask(const float* off, const float* mask, float* y, int B, int HW, cudaStream_t st);
+int launch_maxpool2(const __half* x, __half* y, int B, int H, int W, int C, int x_ld, int y_ld, cudaStream_t st);
+int launch_upsample_add(const __half* x, const float* w, const __half* skip, __half* y, int B, int Hi, int Wi, int C,
+                        int f, int x_ld, int skip_ld, int y_ld, cudaStream_t st);
+int launch_edge_gather(const __half* feat, int feat_ld, int ch_a, int ch_b, const long long* edge_idx, __half* ea,
+                       __half* eb, int B, int H, int W, int K, int out_w, int out_h, cudaStream_t st);
+int launch_edge_head_add(const __half* t, const float* w, const float* bias, int n_out, const long long* edge_idx,
+                         const long long* edge_len, float* out, int out_ctot, int out_ch0, int B, int K, int H, int W,
+                         cudaStream_t st);
+int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st);
+int launch_focal_loss(const float* pred, const float* tgt, long long n, float* out2, cudaStream_t st);
+int launch_decode(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
+                  const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
+                  float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
+                  float* pois, float* result, int* count, cudaStream_t st);
+int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st);
+int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
+                            __half* out, cudaStream_t st);
+int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias, const float* off, const float* mask,
+                              float* y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
+                              int pw, int dh, int dw, int dg, cudaStream_t st);
+}  // namespace mf

@@ -1,0 +1,202 @@
+"""Inference plan builder: turns the (reference-keyed) parameters of the detector into a static list of C-ABI kernel
+launches over pre-allocated NHWC fp16 buffers.
+
+Data layout in HBM: every activation is a row-major [B*H*W, ld] fp16 matrix ("pixel rows"); a logical
+tensor may be a channel slice of a wider buffer, which is how the Root concatenations (dla_dcn.py:195-203) are written
+in place by their producers instead of being copied by torch.cat. Weights are repacked once per plan into
+[n_pad, k_pad] fp16 (k = tap*Cin + c) and eval-mode BatchNorm / InPlaceABN / conv biases are folded into a per-channel
+fp32 (scale, shift) pair applied in the GEMM epilogue.
+"""
+import math
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_OFFMASK = 0, 1, 2, 3
+OUT_F16_NHWC, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
+BN_EPS = 1e-5
+
+
+class Act(object):
+    """Logical NHWC fp16 activation [B,H,W,C]; storage is assigned at Plan.finalize()."""
+
+    def __init__(self, B, H, W, C):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.buf = None      # torch.half tensor [B*H*W, ld]
+        self.owner = None    # concat group this activation is a slice of
+        self.ch_off = 0
+
+    @property
+    def M(self):
+        return self.B * self.H * self.W
+
+    @property
+    def ld(self):
+        return self.buf.shape[1]
+
+    def ptr(self):
+        return self.buf.data_ptr() + 2 * self.ch_off
+
+    def nchw_view(self):
+        """zero-copy torch view [B,C,H,W] (channels-last strides) of this activation."""
+        return self.buf.view(self.B, self.H, self.W, -1)[..., self.ch_off:self.ch_off + self.C].permute(0, 3, 1, 2)
+
+
+class Plan(object):
+    def __init__(self, device):
+        self.device = device
+        self.acts = []
+        self.groups = []     # (total_C, [acts]) concat groups
+        self.ops = []        # (name, fn_name, argbuilder) resolved at finalize
+        self.keep = []       # tensors that must outlive the plan (packed weights, scale/shift, ...)
+        self.launches = []   # (fn, args) after finalize
+        self.n_launch = 0
+
+    # ---- symbolic construction
+    def act(self, B, H, W, C):
+        a = Act(B, H, W, C)
+        self.acts.append(a)
+        return a
+
+    def concat(self, parts):
+        """Return an Act that is the channel concatenation of `parts`, placing every part as a slice of one buffer."""
+        B, H, W = parts[0].B, parts[0].H, parts[0].W
+        total = sum(p.C for p in parts)
+        cat = self.act(B, H, W, total)
+        off = 0
+        for p in parts:
+            assert p.owner is None and (p.B, p.H, p.W) == (B, H, W), "activation already placed in another concat"
+            p.owner, p.ch_off = cat, off
+            off += p.C
+        return cat
+
+    def add(self, fn_name, argbuilder):
+        self.ops.append((fn_name, argbuilder))
+
+    def finalize(self):
+        for a in self.acts:
+            if a.owner is None:
+                a.buf = torch.empty(a.M, a.C, dtype=torch.half, device=self.device)
+        for a in self.acts:
+            if a.owner is not None:
+                root, off = a, 0
+                while root.owner is not None:
+                    off += root.ch_off
+                    root = root.owner
+                a.buf, a.ch_off = root.buf, off
+                a.owner = None
+        lib = _lib.load()
+        for fn_name, argbuilder in self.ops:
+            self.launches.append((getattr(lib, fn_name), tuple(argbuilder()), fn_name))
+        self.n_launch = len(self.launches)
+
+    def run(self):
+        st = torch.cuda.current_stream().cuda_stream
+        for fn, args, name in self.launches:
+            if fn(*args, st) != 0:
+                raise RuntimeError("%s failed: %s" % (name, _lib.load().mf_last_error().decode()))
+
+    # ---- parameter preparation
+    def pack_weight(self, w, cin_pad=None):
+        """OIHW (or OIW for Conv1d) fp32 parameter -> packed fp16 [n_pad, k_pad] device tensor."""
+        w = w.detach().float().contiguous()
+        if w.dim() == 3:
+            w = w.unsqueeze(2)   # Conv1d: [O, I, 1, k]
+        cout, cin, kh, kw = w.shape
+        cin_pad = cin if cin_pad is None else cin_pad
+        bn = _lib.load().mf_conv_block_n(cout)
+        n_pad = (cout + bn - 1) // bn * bn
+        k_pad = (kh * kw * cin_pad + 63) // 64 * 64
+        out = torch.empty(n_pad, k_pad, dtype=torch.half, device=self.device)
+        _lib.call("mf_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr(),
+                  _lib.stream())
+        self.keep.append(out)
+        return out, n_pad, k_pad
+
+    def affine(self, cout, n_pad, bn=None, conv_bias=None, abs_weight=False):
+        """Fold eval-mode BatchNorm (dla_dcn.py:76 etc.) / InPlaceABN (|w|+eps) and the conv bias into (scale, shift)."""
+        scale = torch.ones(n_pad, dtype=torch.float32, device=self.device)
+        shift = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+        if bn is not None:
+            w = bn.weight.detach().float()
+            if abs_weight:
+                w = w.abs() + BN_EPS
+            s = w / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            scale[:cout] = s
+            shift[:cout] = bn.bias.detach().float() - bn.running_mean.detach().float() * s
+        if conv_bias is not None:
+            shift[:cout] += conv_bias.detach().float() * scale[:cout]
+        self.keep.extend([scale, shift])
+        return scale, shift
+
+    # ---- op emitters
+    def conv(self, x, weight, stride, pad, bn=None, bias=None, act=ACT_RELU, residual=None, out=None, abs_weight=False,
+             cin_pad=None):
+        cout, _, kh, kw = weight.shape if weight.dim() == 4 else (weight.shape[0], weight.shape[1], 1, weight.shape[2])
+        wp, n_pad, k_pad = self.pack_weight(weight, cin_pad)
+        scale, shift = self.affine(cout, n_pad, bn, bias, abs_weight)
+        Ho = (x.H + 2 * pad[0] - kh) // stride + 1 if isinstance(pad, tuple) else (x.H + 2 * pad - kh) // stride + 1
+        Wo = (x.W + 2 * pad[1] - kw) // stride + 1 if isinstance(pad, tuple) else (x.W + 2 * pad - kw) // stride + 1
+        assert not isinstance(pad, tuple), "non-square padding is not built"
+        y = out if out is not None else self.act(x.B, Ho, Wo, cout)
+        assert (y.H, y.W, y.C) == (Ho, Wo, cout)
+        cin = x.C
+        self.add("mf_conv2d_nhwc_f16", lambda: (
+            x.ptr(), x.ld, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
+            scale.data_ptr(), shift.data_ptr(), residual.ptr() if residual is not None else None,
+            residual.ld if residual is not None else 0, act, OUT_F16_NHWC, y.ptr(), y.ld))
+        return y
+
+    def conv_to_f32(self, x, weight, bias, out_tensor, out_mode, act, y_ld, stride=1, pad=0, bn=None):
+        """conv whose result leaves the NHWC fp16 world: fp32 NHWC rows (offset/mask) or fp32 NCHW maps (heads)."""
+        cout, _, kh, kw = weight.shape
+        wp, n_pad, k_pad = self.pack_weight(weight)
+        scale, shift = self.affine(cout, n_pad, bn, bias)
+        cin = x.C
+        self.add("mf_conv2d_nhwc_f16", lambda: (
+            x.ptr(), x.ld, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
+            scale.data_ptr(), shift.data_ptr(), None, 0, act, out_mode, out_tensor.data_ptr(), y_ld))
+
+    def dcn(self, x, dcn_mod, bn, out=None):
+        """DeformConv (dla_dcn.py:384-396): conv_offset_mask -> fused gather+contract -> BN -> ReLU."""
+        om = torch.empty(x.M, 32, dtype=torch.float32, device=self.device)
+        self.keep.append(om)
+        self.conv_to_f32(x, dcn_mod.conv_offset_mask.weight, dcn_mod.conv_offset_mask.bias, om, OUT_F32_NHWC,
+                         ACT_OFFMASK, 32, stride=1, pad=1)
+        cout = dcn_mod.weight.shape[0]
+        wp, n_pad, k_pad = self.pack_weight(dcn_mod.weight)
+        scale, shift = self.affine(cout, n_pad, bn, dcn_mod.bias)
+        y = out if out is not None else self.act(x.B, x.H, x.W, cout)
+        cin = x.C
+        self.add("mf_dcn_nhwc_f16", lambda: (
+            x.ptr(), x.ld, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
+            shift.data_ptr(), ACT_RELU, OUT_F16_NHWC, y.ptr(), y.ld))
+        return y
+
+    def maxpool2(self, x, out=None):
+        y = out if out is not None else self.act(x.B, x.H // 2, x.W // 2, x.C)
+        self.add("mf_maxpool2_nhwc_f16", lambda: (x.ptr(), y.ptr(), x.B, x.H, x.W, x.C, x.ld, y.ld))
+        return y
+
+    def upsample_add(self, x, up_weight, skip, f):
+        """depthwise ConvTranspose2d (dla_dcn.py:409-411) fused with `+ layers[i-1]` (:425)."""
+        C, k = up_weight.shape[0], up_weight.shape[2]
+        assert k == 2 * f and C == x.C
+        wt = up_weight.detach().float().reshape(C, k * k).t().contiguous()   # [k*k, C]
+        self.keep.append(wt)
+        y = self.act(x.B, x.H * f, x.W * f, C)
+        self.add("mf_upsample_add_nhwc_f16", lambda: (
+            x.ptr(), wt.data_ptr(), skip.ptr() if skip is not None else None, y.ptr(), x.B, x.H, x.W, C, f, x.ld,
+            skip.ld if skip is not None else 0, y.ld))
+        return y
+
+
+def fingerprint(module):
+    """Cheap change detector for cached plans: parameter/buffer versions + training flag."""
+    v = 0
+    for t in module.parameters():
+        v += t._version
+    for t in module.buffers():
+        v += t._version
+    return (v, module.training, next(module.parameters()).device)

@@ -1,0 +1,185 @@
+"""Multi-branch predictor (reference: model/head/detector_predictor.py:19-169), same registry entry, constructor,
+parameter names and forward(features, targets) -> {'cls', 'reg'}.
+
+Execution (eval): the 9 shared-input 3x3 convs (class_head.0 + reg_features.i.0, 64->256 each) run as ONE implicit GEMM
+with N = 2304 and the InPlaceABN (|gamma|+eps, leaky 0.01) folded into its epilogue; the 1x1 output convs read channel
+slices of that buffer and write the fp32 NCHW `cls` / `reg` maps directly; edge fusion = gather kernel + Conv1d-as-GEMM
++ indexed add; sigmoid_hm is one in-place kernel."""
+import numpy as np
+import torch
+from torch import nn
+
+from ... import engine, registry
+from ..._lib import call, stream
+
+
+class InPlaceABN(nn.Module):
+    """Parameter container with mapillary/inplace_abn's names (weight, bias, running_mean, running_var); semantics
+    y = leaky_relu(BN(x; |weight|+eps, bias), slope) — third-party op, definition unpinned."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, activation="leaky_relu", activation_param=0.01):
+        super(InPlaceABN, self).__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.activation, self.activation_param = activation, activation_param
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+
+
+@registry.PREDICTOR.register("Base_Predictor")
+class _predictor(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super(_predictor, self).__init__()
+        classes = len(cfg.DATASETS.DETECT_CLASSES)
+        self.regression_head_cfg = cfg.MODEL.HEAD.REGRESSION_HEADS
+        self.regression_channel_cfg = cfg.MODEL.HEAD.REGRESSION_CHANNELS
+        self.output_width = cfg.INPUT.WIDTH_TRAIN // cfg.MODEL.BACKBONE.DOWN_RATIO
+        self.output_height = cfg.INPUT.HEIGHT_TRAIN // cfg.MODEL.BACKBONE.DOWN_RATIO
+        self.head_conv = hc = cfg.MODEL.HEAD.NUM_CHANNEL
+        if not cfg.MODEL.INPLACE_ABN:
+            raise NotImplementedError("only the MODEL.INPLACE_ABN=True head of runs/monoflex.yaml:25 is built")
+        mom = cfg.MODEL.HEAD.BN_MOMENTUM
+        self.class_head = nn.Sequential(nn.Conv2d(in_channels, hc, 3, padding=1, bias=False),
+                                        InPlaceABN(hc, momentum=mom), nn.Conv2d(hc, classes, 1, bias=True))
+        self.class_head[-1].bias.data.fill_(-np.log(1 / cfg.MODEL.HEAD.INIT_P - 1))
+        self.reg_features, self.reg_heads = nn.ModuleList(), nn.ModuleList()
+        for idx, keys in enumerate(self.regression_head_cfg):
+            self.reg_features.append(nn.Sequential(nn.Conv2d(in_channels, hc, 3, padding=1, bias=False),
+                                                   InPlaceABN(hc, momentum=mom)))
+            heads = nn.ModuleList()
+            for key_index, key in enumerate(keys):
+                head = nn.Conv2d(hc, self.regression_channel_cfg[idx][key_index], 1, bias=True)
+                if key.find('uncertainty') >= 0 and cfg.MODEL.HEAD.UNCERTAINTY_INIT:
+                    nn.init.xavier_normal_(head.weight, gain=0.01)
+                if key == '3d_offset':
+                    self.offset_index = [idx, key_index]
+                nn.init.constant_(head.bias, 0)
+                heads.append(head)
+            self.reg_heads.append(heads)
+        self.enable_edge_fusion = cfg.MODEL.HEAD.ENABLE_EDGE_FUSION
+        k = cfg.MODEL.HEAD.EDGE_FUSION_KERNEL_SIZE
+        if self.enable_edge_fusion:
+            if cfg.MODEL.HEAD.EDGE_FUSION_NORM != 'BN' or cfg.MODEL.HEAD.EDGE_FUSION_RELU or k != 3:
+                raise NotImplementedError("edge fusion is built for the runs/monoflex.yaml setting (BN, no ReLU, k=3)")
+
+            def trunc(cout):
+                return nn.Sequential(nn.Conv1d(hc, hc, k, padding=k // 2, padding_mode='replicate'),
+                                     nn.BatchNorm1d(hc, momentum=mom), nn.Identity(), nn.Conv1d(hc, cout, 1))
+            self.trunc_heatmap_conv = trunc(classes)
+            self.trunc_offset_conv = trunc(2)
+        self.num_classes = classes
+        self.num_reg = sum(sum(c) for c in self.regression_channel_cfg)
+        self._plans = {}
+
+    # ------------------------------------------------------------------ plan
+    def build_plan(self, feat, K_edge):
+        """feat: engine.Act-like description of the [B,H,W,64] fp16 feature rows."""
+        dev = feat.buf.device
+        P = engine.Plan(dev)
+        B, H, W, hc = feat.B, feat.H, feat.W, self.head_conv
+        x = P.act(B, H, W, feat.C)
+        x.buf, x.ch_off, x.owner = feat.buf, feat.ch_off, None
+        P.acts.remove(x)                                  # externally owned storage
+        branches = [self.class_head] + list(self.reg_features)
+        w_all = torch.cat([b[0].weight.detach() for b in branches], 0)          # [2304, 64, 3, 3]
+
+        class _ABN(object):
+            pass
+        abn = _ABN()
+        abn.weight = torch.cat([b[1].weight.detach() for b in branches])
+        abn.bias = torch.cat([b[1].bias.detach() for b in branches])
+        abn.running_mean = torch.cat([b[1].running_mean for b in branches])
+        abn.running_var = torch.cat([b[1].running_var for b in branches])
+        abn.eps = branches[0][1].eps
+        hid = P.conv(x, w_all, 1, 1, abn, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
+        cls = torch.empty(B, self.num_classes, H, W, dtype=torch.float32, device=dev)
+        reg = torch.empty(B, self.num_reg, H, W, dtype=torch.float32, device=dev)
+
+        def slice_of(i):
+            s = P.act(B, H, W, hc)
+            s.owner, s.ch_off = hid, i * hc
+            return s
+        P.conv_to_f32(slice_of(0), self.class_head[2].weight, self.class_head[2].bias, cls, engine.OUT_F32_NCHW,
+                      engine.ACT_NONE, self.num_classes)
+        ch = 0
+        for i, heads in enumerate(self.reg_heads):
+            src = slice_of(i + 1)
+            for head in heads:
+                P.conv_to_f32(src, head.weight, head.bias, reg[:, ch:], engine.OUT_F32_NCHW, engine.ACT_NONE, self.num_reg)
+                if self.enable_edge_fusion and [i, list(heads).index(head)] == self.offset_index:
+                    off_ch0 = ch
+                ch += head.weight.shape[0]
+        P.edge_idx = torch.zeros(B, K_edge, 2, dtype=torch.long, device=dev)
+        P.edge_len = torch.zeros(B, dtype=torch.long, device=dev)
+        if self.enable_edge_fusion:
+            ea = P.act(B, 1, K_edge + 2, hc)
+            eb = P.act(B, 1, K_edge + 2, hc)
+            oi = self.offset_index[0] + 1
+            ow, oh = self.output_width, self.output_height
+            P.add("mf_edge_gather", lambda: (hid.ptr(), hid.ld, 0, oi * hc, P.edge_idx.data_ptr(), ea.ptr(), eb.ptr(), B,
+                                              H, W, K_edge, ow, oh))
+            for src, seq, dst, ch0, ctot in ((ea, self.trunc_heatmap_conv, cls, 0, self.num_classes),
+                                             (eb, self.trunc_offset_conv, reg, off_ch0, self.num_reg)):
+                t = P.conv(src, seq[0].weight, 1, 0, seq[1], bias=seq[0].bias, act=engine.ACT_NONE)   # [B,1,K,256]
+                w2 = seq[3].weight.detach().float().reshape(seq[3].weight.shape[0], hc).contiguous()
+                b2 = seq[3].bias.detach().float().contiguous()
+                P.keep.extend([w2, b2])
+                n_out = w2.shape[0]
+                P.add("mf_edge_head_add", lambda t=t, w2=w2, b2=b2, n_out=n_out, dst=dst, ch0=ch0, ctot=ctot: (
+                    t.ptr(), w2.data_ptr(), b2.data_ptr(), n_out, P.edge_idx.data_ptr(), P.edge_len.data_ptr(),
+                    dst.data_ptr(), ctot, ch0, B, K_edge, H, W))
+        n_cls = cls.numel()
+        P.add("mf_sigmoid_clamp", lambda: (cls.data_ptr(), n_cls))
+        P.finalize()
+        P.cls, P.reg, P.hidden = cls, reg, hid
+        return P
+
+    def forward(self, features, targets):
+        if self.training:
+            raise NotImplementedError("training path not built yet (no PyTorch fallback)")
+        feat = _as_rows(features)
+        edge_indices = torch.stack([t.get_field("edge_indices") for t in targets])      # B x K x 2   (:138)
+        edge_lens = torch.stack([t.get_field("edge_len") for t in targets]).view(-1)    # B           (:139)
+        K_edge = edge_indices.shape[1]
+        key = (feat.buf.data_ptr(), feat.ch_off, feat.B, feat.H, feat.W, feat.buf.shape[1], K_edge,
+               engine.fingerprint(self))
+        plan = self._plans.get('plan')
+        if plan is None or self._plans.get('key') != key:
+            plan = self.build_plan(feat, K_edge)
+            self._plans = {'plan': plan, 'key': key}
+        plan.edge_idx.copy_(edge_indices, non_blocking=True)
+        plan.edge_len.copy_(edge_lens, non_blocking=True)
+        plan.run()
+        self.last_plan = plan
+        return {'cls': plan.cls, 'reg': plan.reg}
+
+
+class _Rows(object):
+    pass
+
+
+def _as_rows(features):
+    """Accept the backbone's zero-copy channels-last fp16 view, or any [B,C,H,W] CUDA tensor (converted by a kernel)."""
+    if not features.is_cuda:
+        raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
+    B, C, H, W = features.shape
+    r = _Rows()
+    r.B, r.H, r.W, r.C, r.ch_off = B, H, W, C, 0
+    if features.dtype == torch.half and features.stride(1) == 1 and features.stride(3) % 8 == 0 and \
+            features.stride(2) == W * features.stride(3) and features.stride(0) == H * features.stride(2):
+        ld = features.stride(3)
+        base = features.permute(0, 2, 3, 1)                     # [B,H,W,C] view
+        r.ch_off = base.storage_offset() % ld
+        rows = torch.as_strided(base, (B * H * W, ld), (ld, 1), storage_offset=base.storage_offset() - r.ch_off)
+        r.buf = rows
+        return r
+    x = features.float().contiguous()
+    buf = torch.empty(B * H * W, C, dtype=torch.half, device=x.device)
+    call("mf_nchw_f32_to_nhwc_f16", x.data_ptr(), buf.data_ptr(), B, C, H * W, C, stream())
+    r.buf = buf
+    return r
+
+
+def make_predictor(cfg, in_channels):
+    return registry.PREDICTOR[cfg.MODEL.HEAD.PREDICTOR](cfg, in_channels)

@@ -208,3 +208,17 @@ def make_head_logits(batch, out_w=320, out_h=96, seed=2):
     cls = _t(g.standard_normal((batch, NUM_CLASSES, out_h, out_w)) * 1.5 - 3.0)
     reg = _t(g.standard_normal((batch, 50, out_h, out_w)) * 0.5)
     return cls, reg
+
+
+def make_param_lists(tg):
+    """The per-image ParamsList objects engine/inference.py hands to model(images, targets)."""
+    from .structures import Calibration, ParamsList
+    out = []
+    for b in range(len(tg['calib_P'])):
+        t = ParamsList(tg['size'][b], is_train=False)
+        t.add_field('calib', Calibration(tg['calib_P'][b]))
+        t.add_field('pad_size', tg['pad_size'][b])
+        t.add_field('edge_indices', tg['edge_indices'][b])
+        t.add_field('edge_len', tg['edge_len'][b])
+        out.append(t)
+    return out

@@ -1,0 +1,287 @@
+"""-m gpu: per-kernel parity through the C ABI against torch-CPU fp32 on identical fp16-representable operands.
+Tolerances: fp16-output kernels 1e-3 of max|ref| (one fp16 rounding of the result is 4.9e-4); fp32-output kernels 2e-5;
+integer outputs bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+from gpu_util import FakeBN, from_rows, h16, rel_err, set_impl, to_rows
+from monoflex_b200 import engine, synthetic as syn
+from oracle import monoflex_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, act, residual
+    (2, 16, 12, 20, 16, 3, 1, 1, engine.ACT_RELU, False),      # level0-like, N tile 16
+    (2, 16, 12, 20, 32, 3, 2, 1, engine.ACT_RELU, False),      # stride 2, 2 taps per K block
+    (1, 64, 16, 24, 64, 3, 1, 1, engine.ACT_RELU, True),       # BasicBlock conv2 + residual
+    (1, 128, 9, 13, 128, 3, 1, 1, engine.ACT_RELU, False),     # ragged M (117 rows), N tile 128
+    (1, 448, 8, 16, 128, 1, 1, 0, engine.ACT_RELU, False),     # Root 1x1 over a 448-ch concat
+    (1, 32, 8, 16, 64, 1, 1, 0, engine.ACT_NONE, False),       # project 1x1, no activation, K block half empty
+    (1, 64, 10, 12, 256, 3, 1, 1, engine.ACT_LEAKY, False),    # head-like, 2 N tiles, leaky
+    (1, 256, 6, 10, 512, 3, 2, 1, engine.ACT_RELU, False),     # deep layer, 4 N tiles, K = 2304
+]
+
+
+def run_conv(case, impl, seed=0):
+    B, Cin, H, W, Cout, k, stride, pad, act, use_res = case
+    gen = np.random.Generator(np.random.PCG64(seed))
+    x = h16(torch.from_numpy(gen.standard_normal((B, Cin, H, W)).astype(np.float32)))
+    w = h16(torch.from_numpy((gen.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)))
+    bn = FakeBN(Cout, gen)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = h16(torch.from_numpy(gen.standard_normal((B, Cout, Ho, Wo)).astype(np.float32))) if use_res else None
+    set_impl(impl)
+    P = engine.Plan("cuda")
+    xa = P.act(B, H, W, Cin)
+    ra = P.act(B, Ho, Wo, Cout) if use_res else None
+    ya = P.conv(xa, w.cuda(), stride, pad, bn, act=act, residual=ra)
+    P.finalize()
+    xa.buf.copy_(to_rows(x))
+    if use_res:
+        ra.buf.copy_(to_rows(res))
+    P.run()
+    torch.cuda.synchronize()
+    set_impl(0)
+    ref = bn.cpu_apply(F.conv2d(x, w, None, stride, pad))
+    if use_res:
+        ref = ref + res
+    ref = {engine.ACT_RELU: F.relu, engine.ACT_LEAKY: lambda t: F.leaky_relu(t, 0.01), engine.ACT_NONE: lambda t: t}[act](ref)
+    return from_rows(ya), ref
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_crosscheck(case):
+    y, ref = run_conv(case, 1)
+    assert rel_err(y, ref) < 1e-3
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tensor_core(case):
+    y, ref = run_conv(case, 0)
+    assert rel_err(y, ref) < 1e-3
+
+
+def test_stem_7x7_from_image():
+    """base_layer: NCHW fp32 image -> mf_pack_image -> 7x7 conv with Cin padded 3->8."""
+    from monoflex_b200._lib import call, stream
+    gen = np.random.Generator(np.random.PCG64(3))
+    x = h16(torch.from_numpy(gen.standard_normal((2, 3, 20, 36)).astype(np.float32)))
+    w = h16(torch.from_numpy((gen.standard_normal((16, 3, 7, 7)) / 12).astype(np.float32)))
+    bn = FakeBN(16, gen)
+    P = engine.Plan("cuda")
+    xa = P.act(2, 20, 36, 8)
+    ya = P.conv(xa, w.cuda(), 1, 3, bn, cin_pad=8)
+    P.finalize()
+    xc = x.cuda()
+    call("mf_pack_image", xc.data_ptr(), xa.ptr(), 2, 3, 20, 36, stream())
+    P.run()
+    ref = F.relu(bn.cpu_apply(F.conv2d(x, w, None, 1, 3)))
+    assert rel_err(from_rows(ya), ref) < 1e-3
+
+
+DCN_CASES = [(1, 64, 12, 20, 64), (2, 128, 7, 9, 64), (1, 256, 6, 10, 128), (1, 512, 4, 6, 256)]
+
+
+def run_dcn(case, impl, seed=5):
+    B, Cin, H, W, Cout = case
+    gen = np.random.Generator(np.random.PCG64(seed))
+    x = h16(torch.from_numpy(gen.standard_normal((B, Cin, H, W)).astype(np.float32)))
+
+    class D(object):
+        pass
+    d = D()
+    d.weight = h16(torch.from_numpy((gen.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32))).cuda()
+    d.bias = torch.from_numpy((gen.standard_normal(Cout) * 0.1).astype(np.float32)).cuda()
+    d.conv_offset_mask = D()
+    d.conv_offset_mask.weight = h16(torch.from_numpy((gen.standard_normal((27, Cin, 3, 3)) * 1.5 / np.sqrt(9 * Cin)).astype(np.float32))).cuda()
+    d.conv_offset_mask.bias = torch.from_numpy((gen.standard_normal(27) * 0.2).astype(np.float32)).cuda()
+    bn = FakeBN(Cout, gen)
+    set_impl(impl)
+    P = engine.Plan("cuda")
+    xa = P.act(B, H, W, Cin)
+    ya = P.dcn(xa, d, bn)
+    P.finalize()
+    xa.buf.copy_(to_rows(x))
+    P.run()
+    torch.cuda.synchronize()
+    set_impl(0)
+    om_gpu = P.keep[0].cpu()          # [M, 32] offsets + masks produced by the offset conv kernel
+    # oracle on the SAME offsets/mask the GPU produced (isolates the gather+contract kernel) ...
+    off = om_gpu[:, :18].reshape(B, H, W, 18).permute(0, 3, 1, 2).contiguous()
+    mask = om_gpu[:, 18:27].reshape(B, H, W, 9).permute(0, 3, 1, 2).contiguous()
+    cols = h16(mo.dcn_columns(x, off, mask)).reshape(B, Cin * 9, H * W)      # the kernel rounds the blended value to fp16
+    out = torch.matmul(d.weight.cpu().reshape(Cout, -1), cols).view(B, Cout, H, W) + d.bias.cpu().view(1, -1, 1, 1)
+    ref = F.relu(bn.cpu_apply(out))
+    # ... and the offset conv itself against torch
+    om_ref = F.conv2d(x, d.conv_offset_mask.weight.cpu(), d.conv_offset_mask.bias.cpu(), 1, 1)
+    om_ref = torch.cat([om_ref[:, :18], torch.sigmoid(om_ref[:, 18:])], 1)
+    om_got = om_gpu[:, :27].reshape(B, H, W, 27).permute(0, 3, 1, 2)
+    return from_rows(ya), ref, om_got, om_ref
+
+
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_dcn_simt_crosscheck(case):
+    y, ref, om, om_ref = run_dcn(case, 1)
+    assert rel_err(om, om_ref) < 2e-5
+    assert rel_err(y, ref) < 1.5e-3
+
+
+@pytest.mark.parametrize("case", DCN_CASES)
+def test_dcn_tensor_core(case):
+    y, ref, om, om_ref = run_dcn(case, 0)
+    assert rel_err(om, om_ref) < 2e-5
+    assert rel_err(y, ref) < 1.5e-3
+
+
+def test_ext_dcn_v2_forward_fp32_golden_and_kat():
+    """Boundary B: reference _ext signature, exact fp32; golden from the reference's own C loops + testcuda.py KAT."""
+    from monoflex_b200.model.backbone.DCNv2 import _ext
+    from monoflex_b200.model.backbone.DCNv2.dcn_v2 import DCNv2
+    with np.load(os.path.join(GOLDEN, "dcn_op.npz")) as z:
+        g = {k: torch.from_numpy(z[k]).cuda() for k in z.files}
+    y = _ext.dcn_v2_forward(g['x'], g['weight'], g['bias'], g['offset'], g['mask'], 3, 3, 1, 1, 1, 1, 1, 1, 1)
+    assert rel_err(y.cpu(), g['y'].cpu()) < 1e-5
+    # check_zero_offset (testcuda.py:32-67): tolerance 1e-10
+    m = DCNv2(2, 2, (3, 3), stride=1, padding=1, dilation=1, deformable_groups=1).cuda()
+    with torch.no_grad():
+        m.weight.zero_(); m.bias.zero_()
+        m.weight[0, 0, 1, 1] = 1.0; m.weight[1, 1, 1, 1] = 1.0
+        x = torch.randn(2, 2, 4, 4, device="cuda")
+        out = m(x, torch.zeros(2, 18, 4, 4, device="cuda"), torch.full((2, 9, 4, 4), 0.5, device="cuda"))
+    assert (x - 2 * out).abs().max().item() < 1e-10
+    with pytest.raises(RuntimeError):
+        _ext.dcn_v2_forward(g['x'].cpu(), g['weight'], g['bias'], g['offset'], g['mask'], 3, 3, 1, 1, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):
+        _ext.dcn_v2_psroi_pooling_forward()
+
+
+def test_maxpool_and_upsample_add():
+    gen = np.random.Generator(np.random.PCG64(7))
+    x = h16(torch.from_numpy(gen.standard_normal((2, 64, 12, 20)).astype(np.float32)))
+    P = engine.Plan("cuda")
+    xa = P.act(2, 12, 20, 64)
+    pa = P.maxpool2(xa)
+    P.finalize()
+    xa.buf.copy_(to_rows(x))
+    P.run()
+    assert torch.equal(from_rows(pa), F.max_pool2d(x, 2, 2))
+    for f, C in ((2, 64), (4, 64), (2, 128)):
+        xs = h16(torch.from_numpy(gen.standard_normal((2, C, 6, 10)).astype(np.float32)))
+        sk = h16(torch.from_numpy(gen.standard_normal((2, C, 6 * f, 10 * f)).astype(np.float32)))
+        w = torch.from_numpy(gen.uniform(0.0, 1.0, (C, 1, 2 * f, 2 * f)).astype(np.float32))
+        P = engine.Plan("cuda")
+        xa, sa = P.act(2, 6, 10, C), P.act(2, 6 * f, 10 * f, C)
+        ya = P.upsample_add(xa, w.cuda(), sa, f)
+        P.finalize()
+        xa.buf.copy_(to_rows(xs)); sa.buf.copy_(to_rows(sk))
+        P.run()
+        ref = F.conv_transpose2d(xs, w, None, stride=f, padding=f // 2, groups=C) + sk
+        assert rel_err(from_rows(ya), ref) < 1e-3
+
+
+def test_concat_slices_written_in_place():
+    """Root inputs are channel slices of one buffer: producers write them, the 1x1 conv reads the whole row."""
+    gen = np.random.Generator(np.random.PCG64(8))
+    x = h16(torch.from_numpy(gen.standard_normal((1, 32, 8, 12)).astype(np.float32)))
+    w1 = h16(torch.from_numpy((gen.standard_normal((64, 32, 3, 3)) / 17).astype(np.float32)))
+    w2 = h16(torch.from_numpy((gen.standard_normal((64, 64, 3, 3)) / 24).astype(np.float32)))
+    wr = h16(torch.from_numpy((gen.standard_normal((64, 128, 1, 1)) / 11).astype(np.float32)))
+    bn1, bn2, bnr = FakeBN(64, gen), FakeBN(64, gen), FakeBN(64, gen)
+    P = engine.Plan("cuda")
+    xa = P.act(1, 8, 12, 32)
+    a = P.conv(xa, w1.cuda(), 1, 1, bn1)
+    b = P.conv(a, w2.cuda(), 1, 1, bn2, residual=a)
+    cat = P.concat([b, a])
+    r = P.conv(cat, wr.cuda(), 1, 0, bnr)
+    P.finalize()
+    assert a.buf.data_ptr() == b.buf.data_ptr() == cat.buf.data_ptr() and a.ch_off == 64 and b.ch_off == 0
+    xa.buf.copy_(to_rows(x))
+    P.run()
+    ra = h16(F.relu(bn1.cpu_apply(F.conv2d(x, w1, None, 1, 1))))
+    rb = h16(F.relu(bn2.cpu_apply(F.conv2d(ra, w2, None, 1, 1)) + ra))
+    rr = F.relu(bnr.cpu_apply(F.conv2d(torch.cat([rb, ra], 1), wr)))
+    assert rel_err(from_rows(r), rr) < 2e-3
+
+
+def test_decode_bit_exact_vs_golden_and_oracle():
+    from monoflex_b200.model.layers.utils import decode_detections
+    with np.load(os.path.join(GOLDEN, "decode_24x80.npz")) as z:
+        g = {k: torch.from_numpy(z[k]) for k in z.files}
+    cl, rgm = syn.make_head_logits(2, 80, 24)
+    tg = syn.make_targets(2, 80, 24)
+    calib = torch.tensor([[c for c in mo.calib_from_P(P).values()] for P in tg['calib_P']], dtype=torch.float32).cuda()
+    size = torch.tensor(tg['size'], dtype=torch.float32).cuda()
+    dim_mean = torch.tensor(mo.DIM_MEAN).cuda()
+    heat = torch.sigmoid(cl).clamp(1e-4, 1 - 1e-4)
+    for apply_sigmoid, hm in ((False, heat), (True, cl)):
+        for thr in (0.0, 0.2):
+            ws = decode_detections(hm.cuda(), rgm.cuda(), calib, tg['pad_size'].cuda(), size, dim_mean, 50, thr, apply_sigmoid)
+            torch.cuda.synchronize()
+            if not apply_sigmoid:      # identical fp32 heat map -> everything integer is bit exact
+                assert torch.equal(ws.inds.cpu(), g['inds'])
+                assert torch.equal(ws.clses.cpu(), g['clses'])
+                assert torch.equal(ws.ys.cpu(), g['ys']) and torch.equal(ws.xs.cpu(), g['xs'])
+                assert torch.equal(ws.scores.cpu(), g['scores'])
+                for b in range(2):
+                    ref = g['result_b%d_thr%s' % (b, thr)]
+                    n = int(ws.count[b])
+                    assert n == ref.shape[0]
+                    got = ws.result[b, :n].cpu()
+                    assert torch.equal(got[:, 0], ref[:, 0])
+                    assert (got - ref).abs().max() <= 1e-3 * max(1.0, ref.abs().max().item())
+            else:                      # fused sigmoid: same selection (GPU expf differs in the last ulp at most)
+                assert torch.equal(ws.inds.cpu(), g['inds'])
+
+
+def test_decode_full_size_properties():
+    """B=8, 96x320 (BASELINE configs[1]/[3] shape): sortedness, index range, local-max property, agreement with oracle."""
+    from monoflex_b200.model.layers.utils import decode_detections
+    B = 8
+    cl, rgm = syn.make_head_logits(B, 320, 96, seed=21)
+    tg = syn.make_targets(B, 320, 96)
+    calib = torch.tensor([[c for c in mo.calib_from_P(P).values()] for P in tg['calib_P']], dtype=torch.float32).cuda()
+    size = torch.tensor(tg['size'], dtype=torch.float32).cuda()
+    heat = torch.sigmoid(cl).clamp(1e-4, 1 - 1e-4)
+    ws = decode_detections(heat.cuda(), rgm.cuda(), calib, tg['pad_size'].cuda(), size, torch.tensor(mo.DIM_MEAN).cuda(),
+                           50, 0.2)
+    sc, inds = ws.scores.cpu(), ws.inds.cpu()
+    assert (sc[:, :-1] >= sc[:, 1:]).all() and inds.min() >= 0 and inds.max() < 96 * 320
+    res, topk = mo.post_process({'cls': heat, 'reg': rgm}, tg['calib_P'], tg['pad_size'], tg['size'], 0.2)
+    assert torch.equal(inds, topk[1]) and torch.equal(ws.clses.cpu(), topk[2])
+    for b in range(B):
+        n = int(ws.count[b])
+        assert n == res[b].shape[0]
+        assert (ws.result[b, :n].cpu() - res[b]).abs().max() <= 1e-3 * max(1.0, res[b].abs().max().item())
+
+
+def test_nms_topk_tie_rule_and_helpers():
+    from monoflex_b200.model.layers import utils as lu
+    heat = torch.full((1, 3, 8, 8), 1e-4).cuda()
+    sc, inds, cls, ys, xs = lu.select_topk(lu.nms_hm(heat), K=5)
+    assert inds.tolist() == [[0, 1, 2, 3, 4]] and cls.tolist() == [[0.0] * 5]
+    h = torch.rand(2, 3, 24, 80)
+    assert torch.equal(lu.nms_hm(h.cuda()).cpu(), mo.nms_hm(h))
+    reg = torch.randn(2, 50, 24, 80)
+    s2, i2, c2, y2, x2 = lu.select_topk(h.cuda(), K=50)
+    so, io, co, yo, xo = mo.select_topk(mo.nms_hm(h), 50)
+    assert torch.equal(i2.cpu(), io) and torch.equal(c2.cpu(), co)
+    assert torch.equal(lu.select_point_of_interest(2, i2, reg.cuda()).cpu(), mo.gather_pois(reg, io))
+
+
+def test_focal_loss_kernel():
+    from monoflex_b200._lib import call, stream
+    gen = np.random.Generator(np.random.PCG64(12))
+    pred = torch.from_numpy(gen.uniform(1e-4, 1 - 1e-4, (2, 3, 24, 80)).astype(np.float32))
+    tgt = torch.from_numpy((gen.uniform(0, 1, (2, 3, 24, 80)) ** 8).astype(np.float32))
+    tgt.view(-1)[::97] = 1.0
+    out = torch.zeros(2, device="cuda")
+    p, t = pred.cuda(), tgt.cuda()
+    call("mf_focal_loss_forward", p.data_ptr(), t.data_ptr(), p.numel(), out.data_ptr(), stream())
+    loss, npos = mo.focal_loss(pred, tgt)
+    assert abs(out[0].item() - loss.item()) < 1e-4 * abs(loss.item()) and out[1].item() == npos.item()
