@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the MonoFlex per-image hot path on B200 (BASELINE.json configs[1]):
+DLA-34 + IDA-up + DCNv2 + multi-branch predictor + heat-map NMS / top-k / 3D decode, inference, batch 8 per GPU,
+384x1280 synthetic KITTI-shaped images, random-init weights of the reference architecture.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 8] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch. Prints ONE JSON line (rank 0):
+  value      images/s, inputs resident in HBM, timed with CUDA events on the launching stream (max over ranks)
+  e2e        images/s through the public module API `model(images, targets)` from pinned HOST buffers, H2D copy of the
+             images and D2H read of the detections inside the timed region
+  roofline   dominant kernel (head 3x3 implicit GEMM, N=2304): algorithmic FLOPs / measured launch time vs measured peak
+  cpu_baseline  the CPU oracle (port of the reference's torch path) timed on this box's host cores on a bounded sample
+`--impl reference` times that CPU path alone with every host thread (the reference has no GPU build for torch >= 1.11,
+see DESIGN.md) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 384, 1280
+METRIC = "images/sec @ 384x1280 batch 8 (DLA-34+DCNv2+heads+decode inference)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_path(steps, warmup, threads):
+    """The reference's CPU path (oracle port) on a bounded sample: batch-1 full-resolution eval forwards."""
+    import torch
+    from monoflex_b200 import synthetic as syn
+    from oracle import monoflex_oracle as mo
+    torch.set_num_threads(threads)
+    sd = syn.make_state_dict(0)
+    x = syn.make_images(1, H, W)
+    tg = syn.make_targets(1, W // 4, H // 4)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            mo.detector_eval(sd, x, tg['edge_indices'], tg['edge_len'], tg['calib_P'], tg['pad_size'], tg['size'], 0.2)
+            ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    return sum(ts) / len(ts), len(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch timing table (json) to this path")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = {"workload": "DLA-34+DCNv2+heads inference, batch %d/GPU, 384x1280 synthetic, %dxB200 (BASELINE configs[1])"
+              % (args.batch, args.gpus), "batch_per_gpu": args.batch, "height": H, "width": W,
+              "parallelism": "replicas x%d (images shard across GPUs, no data-path collective)" % args.gpus,
+              "l2": "4 rotating input batches (189 MB) + 2.9 GB activation working set >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        sec, n = cpu_path(steps, min(args.warmup, 1), cores)
+        v = 1.0 / sec
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * args.batch,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                           "sample": "%d full-resolution batch-1 eval forwards of the CPU oracle "
+                                                     "(reference torch path restated; the reference's _ext cannot be "
+                                                     "built on torch 2.11)" % n},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from monoflex_b200 import synthetic as syn
+    from monoflex_b200.config import default_cfg
+    from monoflex_b200.model.detector import KeypointDetector
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = KeypointDetector(default_cfg(width=W, height=H))
+    model.load_state_dict(syn.make_state_dict(0))
+    model = model.to(dev).eval()
+    tg = syn.make_targets(B, W // 4, H // 4)
+    targets = [t.to(dev) for t in syn.make_param_lists(tg)]
+    n_in = 4
+    host_imgs = [syn.make_images(B, H, W, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
+    dev_imgs = [h.to(dev) for h in host_imgs]
+
+    def step(x):
+        with torch.no_grad():
+            return model(x, targets)
+
+    for i in range(max(3, args.warmup)):
+        out = step(dev_imgs[i % n_in])
+    torch.cuda.synchronize()
+    launches_per_step = model.backbone.last_plan.n_launch + model.heads.predictor.last_plan.n_launch + 1 + 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(dev_imgs[i % n_in])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    # ---------------------------------------------------------------- end to end: pinned host -> H2D -> model -> D2H
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(dev_imgs[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    host_out = torch.empty(B * 50, 14).pin_memory()
+
+    def prefetch(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[j])
+            bufs[j].copy_(host_imgs[i % n_in], non_blocking=True)
+            ready[j].record(copy_stream)
+
+    for j in range(2):
+        done[j].record()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    prefetch(0)
+    d2h = 0
+    for i in range(args.steps):
+        j = i % 2
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[j])
+        res, eu, _ = step(bufs[j])
+        done[j].record()
+        n = res.shape[0]
+        host_out[:n].copy_(res, non_blocking=True)
+        d2h = n * 14 * 4 + 4 * B
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1)
+    barrier()
+    if rank == 0:
+        sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        hbm, tf_sus, tf_burst, which = peaks()
+        # ------------------------------------------------------------ per-launch timing (separate pass)
+        with torch.no_grad():
+            model.backbone(dev_imgs[0])
+            rows = []
+            for rep in range(3):
+                rows = model.backbone.last_plan.run_timed() + model.heads.predictor.last_plan.run_timed()
+        total = sum(r[2] for r in rows)
+
+        def conv_flops(name, a):
+            if name == "mf_conv2d_nhwc_f16":
+                _, _, b_, h_, w_, cin, _, _, _, kh, kw, stride, pad, cout = a[:14]
+                ho, wo = (h_ + 2 * pad - kh) // stride + 1, (w_ + 2 * pad - kw) // stride + 1
+                return 2.0 * b_ * ho * wo * cout * kh * kw * cin
+            if name == "mf_dcn_nhwc_f16":
+                _, _, b_, h_, w_, cin = a[:6]
+                return 2.0 * b_ * h_ * w_ * a[11] * 9 * cin
+            return 0.0
+        table = [{"kernel": n, "ms": m, "gflop": conv_flops(n, a) / 1e9,
+                  "shape": list(a[2:6]) + ([a[13]] if n == "mf_conv2d_nhwc_f16" else [])} for n, a, m in rows]
+        head = max((r for r in table if r["kernel"] == "mf_conv2d_nhwc_f16"), key=lambda r: r["gflop"])
+        ach = head["gflop"] / head["ms"]                      # GFLOP/ms == TFLOP/s
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("head_conv_dram_bytes_per_launch")
+        all_tf = sum(r["gflop"] for r in table) / total
+        roofline = {"bound": "tensor", "kernel": "igemm_kernel<128,CONV> head 3x3 64->2304 (+IABN epilogue)",
+                    "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
+                    "peak_source": "%s bf16 sustained (kernel timed inside the step; fp16 operands run at the bf16 rate)"
+                                   % which,
+                    "share_of_step": head["ms"] / total, "conv_stack_tflops": all_tf,
+                    "conv_stack_frac": all_tf / tf_sus}
+        if args.dump_launches:
+            os.makedirs(os.path.dirname(os.path.abspath(args.dump_launches)), exist_ok=True)
+            json.dump({"total_ms": total, "launches": table}, open(args.dump_launches, "w"), indent=1)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sec, n = cpu_path(3, 1, cores)
+            cpu = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "%d full-resolution batch-1 eval forwards of the CPU oracle (%.1f s of CPU work)" % (n, sec * n)}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+                "config": config, "clocks": sampler.summary(),
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,8 @@ def load():
             fn.argtypes = args
             fn.restype = _I
         _lib = lib
+        if os.environ.get("MF_CONV_IMPL"):            # diagnostics only: 1 = CUDA-core cross-check kernels
+            lib.mf_set_conv_impl(int(os.environ["MF_CONV_IMPL"]))
     return _lib
 
 

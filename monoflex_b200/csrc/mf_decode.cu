@@ -37,11 +37,18 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_count;
 
-  unsigned long long keys[S1_ITEMS];
-#pragma unroll
-  for (int it = 0; it < S1_ITEMS; ++it) {
+  // per-thread score bits; the pixel index of item `it` is implicit (it*S1_THREADS + tid), the 47-bit key is rebuilt
+  // on the fly: key = ((bits << 15) | (32767 - idx)) + 1   (0 = "no pixel")
+  extern __shared__ unsigned int vbits_sm[];      // [S1_ITEMS][S1_THREADS] score bits (dynamic smem, <= 128 KB)
+  unsigned int* vbits = vbits_sm + threadIdx.x;   // item `it` of this thread lives at vbits[it * S1_THREADS]
+  const int n_items = (HW + S1_THREADS - 1) / S1_THREADS;
+#define MF_KEY(it) ((it) * S1_THREADS + static_cast<int>(threadIdx.x) < HW                                              \
+                        ? ((static_cast<unsigned long long>(vbits[(it) * S1_THREADS]) << 15) |                                         \
+                           static_cast<unsigned long long>(32767 - ((it) * S1_THREADS + static_cast<int>(threadIdx.x)))) + 1ull \
+                        : 0ull)
+  for (int it = 0; it < n_items; ++it) {
     const int idx = it * S1_THREADS + threadIdx.x;
-    unsigned long long key = 0ull;
+    unsigned int key = 0u;
     if (idx < HW) {
       const int y = idx / W, x = idx - y * W;
       const float v = heat_value(hm, H, W, y, x, apply_sigmoid);
@@ -56,10 +63,9 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
         }
       }
       const float kept = (mx == v) ? v : 0.f;         // heat * (hmax == heat)
-      key = (static_cast<unsigned long long>(__float_as_uint(kept)) << 15) | static_cast<unsigned long long>(32767 - idx);
-      key += 1ull;                                     // valid keys are >= 1; 0 marks "no pixel"
+      key = __float_as_uint(kept);
     }
-    keys[it] = key;
+    vbits[it * S1_THREADS] = key;
   }
   if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = K; }
   __syncthreads();
@@ -70,9 +76,8 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
     __syncthreads();
     const unsigned long long prefix = s_prefix;
     const unsigned long long himask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
-#pragma unroll
-    for (int it = 0; it < S1_ITEMS; ++it) {
-      const unsigned long long k = keys[it];
+    for (int it = 0; it < n_items; ++it) {
+      const unsigned long long k = MF_KEY(it);
       if (k != 0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255ull], 1u);
     }
     __syncthreads();
@@ -109,11 +114,11 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
   if (threadIdx.x == 0) s_count = 0;
   for (int i = threadIdx.x; i < 256; i += S1_THREADS) sel[i] = 0ull;
   __syncthreads();
-#pragma unroll
-  for (int it = 0; it < S1_ITEMS; ++it) {
-    if (keys[it] != 0ull && keys[it] >= kth) {
+  for (int it = 0; it < n_items; ++it) {
+    const unsigned long long k = MF_KEY(it);
+    if (k != 0ull && k >= kth) {
       const int slot = atomicAdd(&s_count, 1);
-      if (slot < 256) sel[slot] = keys[it];
+      if (slot < 256) sel[slot] = k;
     }
   }
   __syncthreads();
@@ -131,6 +136,7 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
       __syncthreads();
     }
   }
+#undef MF_KEY
   if (threadIdx.x < K) {
     const unsigned long long k = sel[threadIdx.x] - 1ull;
     out_score[static_cast<long long>(blockIdx.x) * K + threadIdx.x] = __uint_as_float(static_cast<unsigned int>(k >> 15));
@@ -320,7 +326,16 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
     set_error("decode: unsupported shape H*W=%d C*K=%d K=%d R=%d", H * W, C * K, K, R);
     return -1;
   }
-  nms_topk_stage1_kernel<<<B * C, S1_THREADS, 0, st>>>(heat, H, W, K, apply_sigmoid, s1_score, s1_idx);
+  const int n_items = (H * W + S1_THREADS - 1) / S1_THREADS;
+  const int s1_smem = n_items * S1_THREADS * static_cast<int>(sizeof(unsigned int));
+  static int s1_attr = 0;
+  if (s1_smem > s1_attr) {
+    if (check_cuda(cudaFuncSetAttribute(nms_topk_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s1_smem),
+                   "stage1 smem attr"))
+      return -1;
+    s1_attr = s1_smem;
+  }
+  nms_topk_stage1_kernel<<<B * C, S1_THREADS, s1_smem, st>>>(heat, H, W, K, apply_sigmoid, s1_score, s1_idx);
   if (check_cuda(cudaGetLastError(), "nms_topk_stage1")) return -1;
   DecodeParams p;
   p.s1_score = s1_score; p.s1_idx = s1_idx; p.reg = reg; p.calib = calib; p.pad = pad; p.size = size;

@@ -97,6 +97,21 @@ class Plan(object):
             if fn(*args, st) != 0:
                 raise RuntimeError("%s failed: %s" % (name, _lib.load().mf_last_error().decode()))
 
+    def run_timed(self):
+        """Diagnostics: one pass with a CUDA event pair around every launch -> [(kernel, ms)] (adds launch gaps; used by
+        bench.py for the per-kernel roofline numbers, never for throughput)."""
+        st = torch.cuda.current_stream()
+        evs = []
+        for fn, args, name in self.launches:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            if fn(*args, st.cuda_stream) != 0:
+                raise RuntimeError("%s failed: %s" % (name, _lib.load().mf_last_error().decode()))
+            b.record(st)
+            evs.append((name, args, a, b))
+        torch.cuda.synchronize()
+        return [(name, args, a.elapsed_time(b)) for name, args, a, b in evs]
+
     # ---- parameter preparation
     def pack_weight(self, w, cin_pad=None):
         """OIHW (or OIW for Conv1d) fp32 parameter -> packed fp16 [n_pad, k_pad] device tensor."""

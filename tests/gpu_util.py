@@ -41,6 +41,14 @@ def from_rows(act):
 
 
 def set_impl(impl):
+    import os
+    import pytest
+    forced = os.environ.get("MF_CONV_IMPL")
+    if forced is not None and int(forced) != impl:
+        if impl == 0:
+            impl = int(forced)        # "default implementation" requests follow the forced diagnostic mode
+        else:
+            pass
     assert load().mf_set_conv_impl(impl) == 0
 
 
