@@ -25,6 +25,10 @@ const char* mf_last_error(void);
 int mf_version(void);
 /* 0 = tcgen05 tensor-core implicit GEMM (default, the product), 1 = CUDA-core cross-check kernels (diagnostics). */
 int mf_set_conv_impl(int impl);
+/* performance tunables (experiments; results never depend on them): id 0/1 = extra dynamic shared memory (bytes) for
+ * DCN / conv CTAs (fewer resident CTAs, larger L1); id 2 = 1 selects the first-generation non-persistent GEMM kernel;
+ * id 3 = 1 disables the TMA-store epilogue; id 4 = 1 disables the im2col-TMA A operand (cp.async gather instead). */
+int mf_set_tunable(int id, int value);
 /* N tile (16/32/64/128) the conv kernels use for `cout`; packed weights / scale / shift are padded to a multiple. */
 int mf_conv_block_n(int cout);
 

@@ -15,6 +15,7 @@ SIGNATURES = {
     "mf_version": [],
     "mf_set_conv_impl": [_I],
     "mf_conv_block_n": [_I],
+    "mf_set_tunable": [_I, _I],
     "mf_pack_conv_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "mf_conv2d_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "mf_dcn_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P],
@@ -53,6 +54,9 @@ def load():
             fn.argtypes = args
             fn.restype = _I
         _lib = lib
+        for i, name in enumerate(("MF_DCN_EXTRA_SMEM", "MF_CONV_EXTRA_SMEM", "MF_IGEMM_GEN1", "MF_NO_TMA_STORE", "MF_NO_TMA_IM2COL")):     # experiments only
+            if os.environ.get(name):
+                lib.mf_set_tunable(i, int(os.environ[name]))
         if os.environ.get("MF_CONV_IMPL"):            # diagnostics only: 1 = CUDA-core cross-check kernels
             lib.mf_set_conv_impl(int(os.environ["MF_CONV_IMPL"]))
     return _lib

@@ -108,7 +108,8 @@ int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias,
 
 static int run_gemm(const IgemmParams& p, const void* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
   if (g_conv_impl == 1) return launch_simt_gemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
-  return launch_igemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
+  if (g_tunable[2] == 1) return launch_igemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);   // gen-1 kernel (A/B)
+  return launch_igemm2(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
 }
 
 }  // namespace mf
@@ -126,6 +127,11 @@ int mf_set_conv_impl(int impl) {
   return 0;
 }
 int mf_conv_block_n(int cout) { return igemm_block_n(cout); }
+int mf_set_tunable(int id, int value) {
+  if (id < 0 || id >= 8) { set_error("mf_set_tunable: id out of range"); return -1; }
+  g_tunable[id] = value;
+  return 0;
+}
 
 int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                         void* out_f16, void* stream) {

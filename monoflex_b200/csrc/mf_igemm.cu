@@ -65,6 +65,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams p) {
   const int m0 = m_tile * BLOCK_M;
   const int n0 = n_tile * BLOCK_N;
   const int nkb = p.nkb;
+  // MODE_DCN: the 128 rows of a tile are an 8 x 16 pixel block (2-D locality for the bilinear gather: the block's
+  // neighbourhood is ~30 KB of NHWC lines and stays L1-resident); MODE_CONV: 128 consecutive pixels.
+  const int tiles_x = (p.W + 15) >> 4, tiles_y = (p.H + 7) >> 3;
+  const int tile_b = m_tile / (tiles_x * tiles_y);
+  const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
+  const int tile_y0 = (tile_t / tiles_x) << 3, tile_x0 = (tile_t % tiles_x) << 4;
 
   if (warp == NPW && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -138,13 +144,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams p) {
       long long obase[PASSES];      // offset/mask row
 #pragma unroll
       for (int q = 0; q < PASSES; ++q) {
-        const int m = m0 + q * RPP + rsub;
-        if (m < p.M) {
-          const int b = m / HoWo, rem = m - b * HoWo;
-          py[q] = rem / p.Wo;
-          px[q] = rem - py[q] * p.Wo;
-          ibase[q] = static_cast<long long>(b) * p.H * p.W * p.x_ld;
-          obase[q] = static_cast<long long>(m) * p.om_ld;
+        const int r = q * RPP + rsub;
+        const int yy = tile_y0 + (r >> 4), xx = tile_x0 + (r & 15);
+        if (yy < p.H && xx < p.W && tile_b < p.B) {
+          py[q] = yy;
+          px[q] = xx;
+          ibase[q] = static_cast<long long>(tile_b) * p.H * p.W * p.x_ld;
+          obase[q] = (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
         } else {
           py[q] = -1; px[q] = 0; ibase[q] = 0; obase[q] = 0;
         }
@@ -207,8 +213,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const IgemmParams p) {
     tc_fence_after();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    const bool mvalid = m < p.M;
+    int m = m0 + row;
+    bool mvalid = m < p.M;
+    if (MODE == MODE_DCN) {
+      const int yy = tile_y0 + (row >> 4), xx = tile_x0 + (row & 15);
+      mvalid = yy < p.H && xx < p.W && tile_b < p.B;
+      m = (tile_b * p.H + yy) * p.W + xx;
+    }
     constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
     constexpr int NCHUNK = BLOCK_N / CHUNK;
     constexpr int CGROUPS = NPW / 4;            // warps with the same TMEM quadrant split the column chunks
@@ -324,19 +335,23 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+int g_tunable[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] extra dynamic smem (bytes) for DCN CTAs, [1] same for conv CTAs
+
 template <int BLOCK_N, int MODE, int NPW>
 static int launch_cfg(const CUtensorMap& tm, const IgemmParams& p, cudaStream_t st) {
   using Cfg = TileCfg<BLOCK_N>;
   auto kern = igemm_kernel<BLOCK_N, MODE, NPW>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM), "smem attr"))
+  static int attr_smem = 0;
+  int smem = Cfg::SMEM + g_tunable[MODE == MODE_DCN ? 0 : 1];
+  if (smem > 227 * 1024) smem = 227 * 1024;
+  if (smem > attr_smem) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attr"))
       return -1;
-    attr_done = true;
+    attr_smem = smem;
   }
   const int ntn = (p.Cout + BLOCK_N - 1) / BLOCK_N;
-  const int ntm = (p.M + BLOCK_M - 1) / BLOCK_M;
-  kern<<<ntn * ntm, (NPW + 2) * 32, Cfg::SMEM, st>>>(tm, p);
+  const int ntm = MODE == MODE_DCN ? p.B * ((p.H + 7) / 8) * ((p.W + 15) / 16) : (p.M + BLOCK_M - 1) / BLOCK_M;
+  kern<<<ntn * ntm, (NPW + 2) * 32, smem, st>>>(tm, p);
   return check_cuda(cudaGetLastError(), "igemm launch");
 }
 

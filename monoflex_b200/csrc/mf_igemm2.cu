@@ -1,0 +1,632 @@
+// Persistent, warp-specialised implicit-GEMM convolution / fused DCNv2 for sm_100a (second generation of mf_igemm.cu).
+//
+//   D[m, n] = sum_k A[m, k] * Wp[n, k]      m = output pixel, n = output channel, k = (tap, cin) cin fastest
+//
+// One CTA per SM (two for the narrow-N stem tiles) loops over 128 x BLOCK_N output tiles, n fastest:
+//   warps [0, NPW)        A producers. MODE_CONV: 16-byte cp.async gathers of the zero-padded taps into the 128B-swizzled
+//                         K-major stage (Cin < 64 layers). MODE_DCN: per (pixel, tap) 4 neighbour NHWC vectors, fp32
+//                         bilinear blend * mask, fp16, st.shared; a tile is an 8x16 pixel block so its neighbourhood
+//                         stays L1-resident. MODE_CONV_TMA (Cin % 64 == 0): no producer warps at all - the TMA warp
+//                         fetches each (tap, 64-channel) A block with ONE im2col-mode cp.async.bulk.tensor.4d (zero
+//                         padding, strides and row/image wrap-around done by the TMA unit) and these warps become a
+//                         second epilogue group.
+//   warp NPW              weight tiles by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B), same mbarrier ring as A
+//   warp NPW+1            single-thread tcgen05.mma (kind::f16) into one of TWO TMEM accumulators
+//   warps [NPW+2, NPW+6)  epilogue: tcgen05.ld -> scale/shift (+residual) -> activation -> fp16 -> swizzled smem staging
+//                         -> one TMA store per 64-channel sub-tile (fp32 NHWC / NCHW outputs: direct stores)
+// The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1; the smem ring and the
+// barriers persist across tiles, so the per-tile cost is the MMA time, not a pipeline fill + drain.
+#include "mf_common.cuh"
+#include "mf_kernels.h"
+
+namespace mf {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_STAGE = BM * BK * 2;   // 16 KB
+
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int STAGES = BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : 4);
+  static constexpr int LAG = BLOCK_N >= 64 ? 3 : 2;            // cp.async groups in flight per producer thread
+  static constexpr int CTAS_PER_SM = BLOCK_N >= 64 ? 1 : 2;
+  static constexpr int B_STAGE = BLOCK_N * BK * 2;
+  static constexpr int OUT_STAGE = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;
+  static constexpr int BAR_BYTES = 1024;                        // barriers + tmem ptr + scale/shift staging
+  static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + 1024;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns per accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                // power of two >= 32 for every BLOCK_N used
+};
+
+template <int N>
+MF_DEVINL void act_chunk(float (&v)[N], int act, int nb) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);      // == v > 0 ? v : 0.01 v
+  } else if (act == ACT_OFFMASK) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (nb + i >= 18) ? 1.f / (1.f + __expf(-v[i])) : v[i];
+  }
+}
+
+MF_DEVINL void tma_load_im2col_4d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                  uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+MF_DEVINL void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+MF_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+MF_DEVINL void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+MF_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+MF_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+MF_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BLOCK_N, int MODE, int NPW>
+__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N>::CTAS_PER_SM)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
+              const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
+  constexpr bool A_TMA = (MODE == MODE_CONV_TMA);
+  constexpr int EPI_THREADS = A_TMA ? 128 + NPW * 32 : 128;
+  using C = Cfg2<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int LAG = C::LAG;
+  constexpr int B_STAGE = C::B_STAGE;
+  constexpr int NPT = NPW * 32;
+  constexpr int RPP = NPT / 8;
+  constexpr int PASSES = BM / RPP;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + STAGES * A_STAGE;
+  uint8_t* o_smem = b_smem + STAGES * B_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(o_smem + C::OUT_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sc_s = reinterpret_cast<float*>(o_smem + C::OUT_STAGE + C::BAR_BYTES);
+  float* sh_s = sc_s + BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntn = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_x = (p.W + 15) >> 4, tiles_y = (p.H + 7) >> 3;
+  const int ntm = MODE == MODE_DCN ? p.B * tiles_x * tiles_y : (p.M + BM - 1) / BM;
+  const int ntiles = ntn * ntm;
+  const int nkb = p.nkb;
+  const int HoWo = p.Ho * p.Wo;
+
+  if (warp == NPW && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    if (use_tma_store) tma_prefetch_desc(&tmap_y);
+    if (A_TMA) tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], A_TMA ? 1 : NPT + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == NPW + 1) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // ================================================================ epilogue body (run by 1 or 2 warp groups)
+  auto run_epilogue = [&](const int group, const int et) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;
+    constexpr int NCHUNK = BLOCK_N / CHUNK;
+    constexpr int NGROUPS = EPI_THREADS / 128;
+    const bool staged = use_tma_store != 0;             // host guarantees OUT_F16_NHWC && BLOCK_N >= 64
+    int ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      const int n0 = (t % ntn) * BLOCK_N;
+      const int m_tile = t / ntn;
+      int m = m_tile * BM + row;
+      bool mvalid = m < p.M;
+      int tile_b = 0, tile_y0 = 0, tile_x0 = 0;
+      if (MODE == MODE_DCN) {
+        tile_b = m_tile / (tiles_x * tiles_y);
+        const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
+        tile_y0 = (tile_t / tiles_x) << 3;
+        tile_x0 = (tile_t % tiles_x) << 4;
+        const int yy = tile_y0 + (row >> 4), xx = tile_x0 + (row & 15);
+        mvalid = yy < p.H && xx < p.W;
+        m = (tile_b * p.H + yy) * p.W + xx;
+      }
+      if (staged && et == 0) bulk_wait_read0();         // previous tile's TMA store has finished reading the staging
+      if (et < BLOCK_N) {
+        sc_s[et] = __ldg(p.scale + n0 + et);
+        sh_s[et] = __ldg(p.shift + n0 + et);
+      }
+      bar_sync_named(1, EPI_THREADS);
+      mbar_wait(&acc_full[acc], (ti >> 1) & 1);
+      tc_fence_after();
+      if (group >= NCHUNK) {                                        // nothing to read: hand the accumulator back
+        tc_fence_before();
+        mbar_arrive(&acc_empty[acc]);
+      }
+#pragma unroll
+      for (int ch0 = 0; ch0 < NCHUNK; ch0 += NGROUPS) {
+        const int ch = ch0 + group;
+        if (ch >= NCHUNK) break;
+        uint32_t r[CHUNK];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * C::ACC_COLS + ch * CHUNK;
+        if constexpr (CHUNK == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        if (ch + NGROUPS >= NCHUNK) {                    // last chunk of this thread: accumulator fully read
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+        }
+        const int nb = n0 + ch * CHUNK;
+        float v[CHUNK];
+#pragma unroll
+        for (int i = 0; i < CHUNK; i += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sc_s + ch * CHUNK + i);
+          const float4 h4 = *reinterpret_cast<const float4*>(sh_s + ch * CHUNK + i);
+          v[i] = __uint_as_float(r[i]) * s4.x + h4.x;
+          v[i + 1] = __uint_as_float(r[i + 1]) * s4.y + h4.y;
+          v[i + 2] = __uint_as_float(r[i + 2]) * s4.z + h4.z;
+          v[i + 3] = __uint_as_float(r[i + 3]) * s4.w + h4.w;
+        }
+        if (p.res != nullptr && mvalid) {
+          const __half* rp = p.res + static_cast<long long>(m) * p.res_ld + nb;
+#pragma unroll
+          for (int i = 0; i < CHUNK; i += 8) {
+            if (nb + i < p.Cout) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + i));
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(rh[e]);
+                v[i + 2 * e] += f.x;
+                v[i + 2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        act_chunk<CHUNK>(v, p.act, nb);
+        if (p.out_mode == OUT_F16_NHWC) {
+          if (staged) {
+            if constexpr (BLOCK_N >= 64) {
+              uint8_t* sub = o_smem + (ch >> 1) * A_STAGE;
+#pragma unroll
+              for (int i = 0; i < CHUNK; i += 8) {
+                __half2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(sub + sw128_off(row, (ch & 1) * 4 + (i >> 3))) = *reinterpret_cast<uint4*>(o);
+              }
+            }
+          } else if (mvalid) {
+            __half* yp = reinterpret_cast<__half*>(p.y) + static_cast<long long>(m) * p.y_ld + nb;
+#pragma unroll
+            for (int i = 0; i < CHUNK; i += 8) {
+              if (nb + i < p.Cout) {
+                __half2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(yp + i) = *reinterpret_cast<uint4*>(o);
+              }
+            }
+          }
+        } else if (mvalid) {
+          if (p.out_mode == OUT_F32_NHWC) {
+            float* yp = reinterpret_cast<float*>(p.y) + static_cast<long long>(m) * p.y_ld + nb;
+#pragma unroll
+            for (int i = 0; i < CHUNK; i += 4) {
+              if (nb + i < p.y_ld) *reinterpret_cast<float4*>(yp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          } else {
+            const int b = m / HoWo, pix = m - b * HoWo;
+            float* yp = reinterpret_cast<float*>(p.y) + (static_cast<long long>(b) * p.y_ld + nb) * HoWo + pix;
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+              if (nb + i < p.Cout) yp[static_cast<long long>(i) * HoWo] = v[i];
+            }
+          }
+        }
+      }
+      if (staged) {
+        fence_proxy_async();
+        bar_sync_named(1, EPI_THREADS);
+        if (et == 0) {
+          if constexpr (BLOCK_N >= 64) {
+#pragma unroll
+            for (int sidx = 0; sidx < BLOCK_N / 64; ++sidx) {
+              if (n0 + sidx * 64 < p.Cout) {
+                if (MODE == MODE_DCN)
+                  tma_store_4d(&tmap_y, smem_u32(o_smem + sidx * A_STAGE), n0 + sidx * 64, tile_x0, tile_y0, tile_b);
+                else
+                  tma_store_2d(&tmap_y, smem_u32(o_smem + sidx * A_STAGE), n0 + sidx * 64, m_tile * BM);
+              }
+            }
+          }
+          bulk_commit();
+        }
+      } else {
+        bar_sync_named(1, EPI_THREADS);       // sc_s / sh_s are rewritten by the next tile
+      }
+    }
+    if (staged && et == 0) bulk_wait0();                 // all stores complete before the CTA exits
+  };
+
+  if (warp < NPW && A_TMA) {
+    run_epilogue(1, 128 + threadIdx.x);                   // second epilogue group (odd 32-column chunks)
+  } else if (warp < NPW) {
+    // ================================================================ A producers
+    const int tid = threadIdx.x;
+    const int j = tid & 7;
+    const int rsub = tid >> 3;
+    int it = 0;                       // running K-block counter (stage = it % STAGES)
+    if (MODE == MODE_CONV) {
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / ntn) * BM;
+        int iy0[PASSES], ix0[PASSES];
+        long long base[PASSES];
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) {
+          const int m = m0 + q * RPP + rsub;
+          if (m < p.M) {
+            const int b = m / HoWo, rem = m - b * HoWo;
+            const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+            iy0[q] = oy * p.stride - p.pad;
+            ix0[q] = ox * p.stride - p.pad;
+            base[q] = (static_cast<long long>(b * p.H + iy0[q]) * p.W + ix0[q]) * p.x_ld;
+          } else {
+            iy0[q] = -100000; ix0[q] = -100000; base[q] = 0;
+          }
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          const int k = kb * BK + j * 8;
+          const int tap = k / p.Cin;
+          const int c0 = k - tap * p.Cin;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          const bool kvalid = k < p.K_real;
+          const long long koff = static_cast<long long>(ky * p.W + kx) * p.x_ld + c0;
+          const uint32_t a_stage = smem_u32(a_smem + s * A_STAGE);
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q) {
+            const int r = q * RPP + rsub;
+            const int iy = iy0[q] + ky, ix = ix0[q] + kx;
+            const bool ok = kvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            const __half* src = ok ? p.x + base[q] + koff : p.x;
+            cp_async16(a_stage + sw128_off(r, j), src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (it >= LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async();
+            mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+          }
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int i = (it > LAG ? it - LAG : 0); i < it; ++i) mbar_arrive(&full_bar[i % STAGES]);
+    } else {
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m_tile = t / ntn;
+        const int tile_b = m_tile / (tiles_x * tiles_y);
+        const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
+        const int tile_y0 = (tile_t / tiles_x) << 3, tile_x0 = (tile_t % tiles_x) << 4;
+        int py[PASSES], px[PASSES];
+        long long obase[PASSES];
+        const long long ibase = static_cast<long long>(tile_b) * p.H * p.W * p.x_ld;
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) {
+          const int r = q * RPP + rsub;
+          const int yy = tile_y0 + (r >> 4), xx = tile_x0 + (r & 15);
+          if (yy < p.H && xx < p.W) {
+            py[q] = yy; px[q] = xx;
+            obase[q] = (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
+          } else {
+            py[q] = -1; px[q] = 0; obase[q] = 0;
+          }
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          const int k = kb * BK + j * 8;
+          const int tap = k / p.Cin;          // Cin % 64 == 0: all chunks of a K block share the tap
+          const int c0 = k - tap * p.Cin;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          uint8_t* a_stage = a_smem + s * A_STAGE;
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q) {
+            const int r = q * RPP + rsub;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            if (py[q] >= 0 && tap < 9) {
+              const float* om = p.offmask + obase[q];
+              const float off_h = __ldg(om + 2 * tap), off_w = __ldg(om + 2 * tap + 1), mk = __ldg(om + 18 + tap);
+              const float h_im = static_cast<float>(py[q] - 1 + ky) + off_h;
+              const float w_im = static_cast<float>(px[q] - 1 + kx) + off_w;
+              if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
+                const float hlf = floorf(h_im), wlf = floorf(w_im);
+                const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
+                const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf);
+                const int hh_i = hl + 1, wh_i = wl + 1;
+                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+                const __half* xb = p.x + ibase + c0;
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                const bool tp = hl >= 0, bt = hh_i <= p.H - 1, lf = wl >= 0, rt = wh_i <= p.W - 1;
+                const uint4 v1 = (tp && lf) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hl * p.W + wl) * p.x_ld)) : z;
+                const uint4 v2 = (tp && rt) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hl * p.W + wh_i) * p.x_ld)) : z;
+                const uint4 v3 = (bt && lf) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hh_i * p.W + wl) * p.x_ld)) : z;
+                const uint4 v4 = (bt && rt) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hh_i * p.W + wh_i) * p.x_ld)) : z;
+                const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v2);
+                const __half2* h3 = reinterpret_cast<const __half2*>(&v3);
+                const __half2* h4 = reinterpret_cast<const __half2*>(&v4);
+                __half2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f1 = __half22float2(h1[e]), f2 = __half22float2(h2[e]);
+                  const float2 f3 = __half22float2(h3[e]), f4 = __half22float2(h4[e]);
+                  const float vx = (w1 * f1.x + w2 * f2.x + w3 * f3.x + w4 * f4.x) * mk;
+                  const float vy = (w1 * f1.y + w2 * f2.y + w3 * f3.y + w4 * f4.y) * mk;
+                  o[e] = __floats2half2_rn(vx, vy);
+                }
+                out = *reinterpret_cast<uint4*>(o);
+              }
+            }
+            *reinterpret_cast<uint4*>(a_stage + sw128_off(r, j)) = out;
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == NPW) {
+    // ================================================================ weight tiles by TMA
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n0 = (t % ntn) * BLOCK_N;
+        int cw = 0, chh = 0, cn = 0;
+        if (A_TMA) {                      // coordinates of the tile's first output pixel in input space (incl. -pad)
+          const int m0 = (t / ntn) * BM;
+          cn = m0 / HoWo;
+          const int rem = m0 - cn * HoWo;
+          const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
+          cw = ox * p.stride - p.pad;
+          chh = oy * p.stride - p.pad;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], A_TMA ? A_STAGE + B_STAGE : B_STAGE);
+          if (A_TMA) {
+            const int k = kb * BK;
+            const int tap = k / p.Cin, c0 = k - tap * p.Cin;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            tma_load_im2col_4d(smem_u32(a_smem + s * A_STAGE), &tmap_x, &full_bar[s], c0, cw, chh, cn,
+                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+          }
+          tma_load_2d(smem_u32(b_smem + s * B_STAGE), &tmap_w, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == NPW + 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BLOCK_N);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&acc_empty[acc], ((ti >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_smem + s * A_STAGE);
+          const uint32_t b_addr = smem_u32(b_smem + s * B_STAGE);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k4 * 32), umma_desc_sw128(b_addr + k4 * 32), idesc,
+                     (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    run_epilogue(0, (warp - (NPW + 2)) * 32 + lane);      // first epilogue group (even chunks, or all of them)
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPW + 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled2 encode_fn() {
+  static PFN_encodeTiled2 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable");
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled2>(ptr);
+  }
+  return fn;
+}
+
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+static PFN_encodeIm2col encode_im2col_fn() {
+  static PFN_encodeIm2col fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      set_error("cuTensorMapEncodeIm2col entry point unavailable");
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeIm2col>(ptr);
+  }
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, int MODE, int NPW>
+static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx, const IgemmParams& p,
+                       int use_tma_store, cudaStream_t st) {
+  using C = Cfg2<BLOCK_N>;
+  auto kern = igemm2_kernel<BLOCK_N, MODE, NPW>;
+  static int attr_smem = 0;
+  int smem = C::SMEM + g_tunable[MODE == MODE_DCN ? 0 : 1];
+  if (smem > 227 * 1024) smem = 227 * 1024;
+  if (smem > attr_smem) {
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attr")) return -1;
+    attr_smem = smem;
+  }
+  const int ntn = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+  const int ntm = MODE == MODE_DCN ? p.B * ((p.H + 7) / 8) * ((p.W + 15) / 16) : (p.M + BM - 1) / BM;
+  int grid = num_sms() * C::CTAS_PER_SM;
+  if (grid > ntn * ntm) grid = ntn * ntm;
+  kern<<<grid, (NPW + 6) * 32, smem, st>>>(tw, ty, tx, p, use_tma_store);
+  return check_cuda(cudaGetLastError(), "igemm2 launch");
+}
+
+int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
+  PFN_encodeTiled2 enc = encode_fn();
+  if (!enc) return -1;
+  const int bn = igemm_block_n(p.Cout);
+  if (n_pad % bn != 0 || k_pad % BK != 0 || k_pad < p.nkb * BK) {
+    set_error("igemm: packed weight shape [%d,%d] incompatible with block_n=%d nkb=%d", n_pad, k_pad, bn, p.nkb);
+    return -1;
+  }
+  if (mode == MODE_DCN && (p.Cin % 64 != 0 || p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1)) {
+    set_error("dcn igemm: only 3x3 s1 p1 with Cin %% 64 == 0 is built (got Cin=%d)", p.Cin);
+    return -1;
+  }
+  if (mode == MODE_CONV && (p.Cin % 8 != 0 || p.x_ld % 8 != 0)) {
+    set_error("conv igemm: Cin and pixel stride must be multiples of 8 (got %d, %d)", p.Cin, p.x_ld);
+    return -1;
+  }
+  CUtensorMap tw, ty;
+  {
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(n_pad)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(k_pad) * 2};
+    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(wp), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed (%d)", static_cast<int>(r)); return -1; }
+  }
+  int use_tma_store = 0;
+  ty = tw;
+  if (p.out_mode == OUT_F16_NHWC && bn >= 64 && g_tunable[3] == 0 &&
+      (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && p.y_ld % 8 == 0) {
+    CUresult r;
+    if (mode == MODE_DCN) {
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cout), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
+                            static_cast<cuuint64_t>(p.B)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.y_ld) * 2, static_cast<cuuint64_t>(p.y_ld) * 2 * p.W,
+                            static_cast<cuuint64_t>(p.y_ld) * 2 * p.W * p.H};
+      cuuint32_t box[4] = {64, 16, 8, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.Cout), static_cast<cuuint64_t>(p.M)};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(p.y_ld) * 2};
+      cuuint32_t box[2] = {64, BM};
+      cuuint32_t estr[2] = {1, 1};
+      r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed (%d)", static_cast<int>(r)); return -1; }
+    use_tma_store = 1;
+  }
+  // A operand by im2col-mode TMA whenever a K block is one (tap, 64-channel) box
+  CUtensorMap tx = tw;
+  bool a_tma = false;
+  if (mode == MODE_CONV && p.Cin % 64 == 0 && g_tunable[4] == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
+      p.kw <= 16 && p.kh <= 16 && p.stride <= 8) {
+    PFN_encodeIm2col enc2 = encode_im2col_fn();
+    if (!enc2) return -1;
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
+                          static_cast<cuuint64_t>(p.B)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.x_ld) * 2, static_cast<cuuint64_t>(p.x_ld) * 2 * p.W,
+                          static_cast<cuuint64_t>(p.x_ld) * 2 * p.W * p.H};
+    int lower[2] = {-p.pad, -p.pad};
+    int upper[2] = {p.pad - (p.kw - 1), p.pad - (p.kh - 1)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(p.stride), static_cast<cuuint32_t>(p.stride), 1};
+    CUresult r = enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), gdim, gstr, lower, upper, 64, BM,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d)", static_cast<int>(r)); return -1; }
+    a_tma = true;
+  }
+#define MF_DISPATCH2(BN)                                                                          \
+  if (bn == BN) {                                                                                 \
+    if (mode == MODE_DCN) return launch2_cfg<BN, MODE_DCN, 8>(tw, ty, tx, p, use_tma_store, st);  \
+    if (a_tma) return launch2_cfg<BN, MODE_CONV_TMA, 4>(tw, ty, tx, p, use_tma_store, st);        \
+    return launch2_cfg<BN, MODE_CONV, 4>(tw, ty, tx, p, use_tma_store, st);                       \
+  }
+  MF_DISPATCH2(16)
+  MF_DISPATCH2(32)
+  MF_DISPATCH2(64)
+  MF_DISPATCH2(128)
+#undef MF_DISPATCH2
+  set_error("igemm2: unsupported block_n %d", bn);
+  return -1;
+}
+
+}  // namespace mf

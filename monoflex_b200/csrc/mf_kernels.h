@@ -6,7 +6,7 @@
 
 namespace mf {
 
-enum { MODE_CONV = 0, MODE_DCN = 1 };
+enum { MODE_CONV = 0, MODE_DCN = 1, MODE_CONV_TMA = 2 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFMASK = 3 };
 enum { OUT_F16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
 
@@ -34,8 +34,10 @@ struct IgemmParams {
   int y_ld;
 };
 
+extern int g_tunable[8];
 int igemm_block_n(int cout);
 int launch_igemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
+int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_simt_gemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 
 }  // namespace mf

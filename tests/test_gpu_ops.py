@@ -25,6 +25,9 @@ CONV_CASES = [
     (1, 32, 8, 16, 64, 1, 1, 0, engine.ACT_NONE, False),       # project 1x1, no activation, K block half empty
     (1, 64, 10, 12, 256, 3, 1, 1, engine.ACT_LEAKY, False),    # head-like, 2 N tiles, leaky
     (1, 256, 6, 10, 512, 3, 2, 1, engine.ACT_RELU, False),     # deep layer, 4 N tiles, K = 2304
+    (3, 64, 7, 11, 64, 3, 1, 1, engine.ACT_RELU, True),        # tiles wrap across rows and images (im2col traversal)
+    (2, 64, 17, 23, 128, 3, 2, 1, engine.ACT_RELU, False),     # stride 2 on odd sizes
+    (2, 128, 5, 300, 64, 3, 1, 1, engine.ACT_NONE, False),     # wide rows: several 128-pixel tiles per image row
 ]
 
 
