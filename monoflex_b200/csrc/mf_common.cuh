@@ -131,6 +131,13 @@ MF_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::
 MF_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// generic K-major descriptor: layout_type 0 = no swizzle (LBO = byte distance between the two 16-byte K chunks of an MMA,
+// SBO = distance between 8-row groups), 6 / 4 / 2 = 32B / 64B / 128B swizzle (LBO ignored, SBO = 8 * row bytes)
+MF_DEVINL uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) |
+         (static_cast<uint64_t>(layout_type) << 61);
+}
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 MF_DEVINL constexpr uint32_t umma_idesc_f16(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);

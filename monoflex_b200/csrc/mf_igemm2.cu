@@ -25,15 +25,17 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE = BM * BK * 2;   // 16 KB
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 struct Cfg2 {
-  static constexpr int STAGES = BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : 4);
+  static constexpr int STAGES = MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : 4));
   static constexpr int LAG = BLOCK_N >= 64 ? 3 : 2;            // cp.async groups in flight per producer thread
   static constexpr int CTAS_PER_SM = BLOCK_N >= 64 ? 1 : 2;
   static constexpr int B_STAGE = BLOCK_N * BK * 2;
   static constexpr int OUT_STAGE = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;
   static constexpr int BAR_BYTES = 1024;                        // barriers + tmem ptr + scale/shift staging
-  static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + 1024;
+  static constexpr int PRM_BYTES = MODE == MODE_DCN ? 9 * BM * 32 : 0;   // DCN sampling records
+  static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + PRM_BYTES + 1024;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;                // power of two >= 32 for every BLOCK_N used
 };
@@ -80,12 +82,12 @@ MF_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0
 MF_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int BLOCK_N, int MODE, int NPW>
-__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N>::CTAS_PER_SM)
+__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE>::CTAS_PER_SM)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
               const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
   constexpr bool A_TMA = (MODE == MODE_CONV_TMA);
   constexpr int EPI_THREADS = A_TMA ? 128 + NPW * 32 : 128;
-  using C = Cfg2<BLOCK_N>;
+  using C = Cfg2<BLOCK_N, MODE>;
   constexpr int STAGES = C::STAGES;
   constexpr int LAG = C::LAG;
   constexpr int B_STAGE = C::B_STAGE;
@@ -105,6 +107,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sc_s = reinterpret_cast<float*>(o_smem + C::OUT_STAGE + C::BAR_BYTES);
   float* sh_s = sc_s + BLOCK_N;
+  uint8_t* prm_smem = reinterpret_cast<uint8_t*>(sh_s + BLOCK_N);      // MODE_DCN only: 9*128 sampling records (36 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -333,82 +336,98 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       fence_proxy_async();
       for (int i = (it > LAG ? it - LAG : 0); i < it; ++i) mbar_arrive(&full_bar[i % STAGES]);
     } else {
+      // ---------------------------------------------------------- DCNv2 (3x3, stride 1, pad 1, dil 1, dg 1)
+      // Phase P, once per tile: every (pixel, tap) gets its sampling record - 4 bilinear weights already multiplied by
+      // the modulation mask (0 for corners / samples outside the image, dcn_v2_im2col_cuda.cu:37-48,180) and the 4
+      // corner pixel indices (clamped, so the gather needs no predication). The reference recomputes this per channel;
+      // the first version of this kernel per 8-channel chunk. Phase G then is pure load / blend / store.
+      float4* prm_w = reinterpret_cast<float4*>(prm_smem);
+      int4* prm_o = reinterpret_cast<int4*>(prm_smem + 9 * BM * 16);
+      int stage = 0;
+      uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m_tile = t / ntn;
         const int tile_b = m_tile / (tiles_x * tiles_y);
         const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
         const int tile_y0 = (tile_t / tiles_x) << 3, tile_x0 = (tile_t % tiles_x) << 4;
-        int py[PASSES], px[PASSES];
-        long long obase[PASSES];
-        const long long ibase = static_cast<long long>(tile_b) * p.H * p.W * p.x_ld;
-#pragma unroll
-        for (int q = 0; q < PASSES; ++q) {
-          const int r = q * RPP + rsub;
+        bar_sync_named(2, NPT);                              // previous tile's gather no longer reads the records
+        for (int item = tid; item < 9 * BM; item += NPT) {
+          const int tap = item >> 7, r = item & (BM - 1);
           const int yy = tile_y0 + (r >> 4), xx = tile_x0 + (r & 15);
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+          int4 o = make_int4(0, 0, 0, 0);
           if (yy < p.H && xx < p.W) {
-            py[q] = yy; px[q] = xx;
-            obase[q] = (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
-          } else {
-            py[q] = -1; px[q] = 0; obase[q] = 0;
+            const float* om = p.offmask + (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const float h_im = static_cast<float>(yy - 1 + ky) + __ldg(om + 2 * tap);
+            const float w_im = static_cast<float>(xx - 1 + kx) + __ldg(om + 2 * tap + 1);
+            if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
+              const float mk = __ldg(om + 18 + tap);
+              const float hlf = floorf(h_im), wlf = floorf(w_im);
+              const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
+              const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf), hi = hl + 1, wi = wl + 1;
+              const bool tp = hl >= 0, bt = hi <= p.H - 1, lf = wl >= 0, rt = wi <= p.W - 1;
+              w.x = (tp && lf) ? hh * hw * mk : 0.f;
+              w.y = (tp && rt) ? hh * lw * mk : 0.f;
+              w.z = (bt && lf) ? lh * hw * mk : 0.f;
+              w.w = (bt && rt) ? lh * lw * mk : 0.f;
+              const int hlc = max(hl, 0), hic = min(hi, p.H - 1), wlc = max(wl, 0), wic = min(wi, p.W - 1);
+              o = make_int4(hlc * p.W + wlc, hlc * p.W + wic, hic * p.W + wlc, hic * p.W + wic);
+            }
           }
+          prm_w[item] = w;
+          prm_o[item] = o;
         }
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          const int k = kb * BK + j * 8;
-          const int tap = k / p.Cin;          // Cin % 64 == 0: all chunks of a K block share the tap
-          const int c0 = k - tap * p.Cin;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          uint8_t* a_stage = a_smem + s * A_STAGE;
+        bar_sync_named(2, NPT);
+        const __half* x_img = p.x + static_cast<long long>(tile_b) * p.H * p.W * p.x_ld + j * 8;
+        int tap = 0, c0 = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_stage = a_smem + stage * A_STAGE;
+          uint4 v[PASSES][4];
+          float4 wq[PASSES];
+#pragma unroll
+          for (int q = 0; q < PASSES; ++q) {               // all loads of the K block first (memory-level parallelism)
+            const int r = q * RPP + rsub;
+            wq[q] = prm_w[tap * BM + r];
+            const int4 o = prm_o[tap * BM + r];
+            const __half* xb = x_img + c0;
+            v[q][0] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.x) * p.x_ld));
+            v[q][1] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.y) * p.x_ld));
+            v[q][2] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.z) * p.x_ld));
+            v[q][3] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.w) * p.x_ld));
+          }
 #pragma unroll
           for (int q = 0; q < PASSES; ++q) {
             const int r = q * RPP + rsub;
-            uint4 out = make_uint4(0u, 0u, 0u, 0u);
-            if (py[q] >= 0 && tap < 9) {
-              const float* om = p.offmask + obase[q];
-              const float off_h = __ldg(om + 2 * tap), off_w = __ldg(om + 2 * tap + 1), mk = __ldg(om + 18 + tap);
-              const float h_im = static_cast<float>(py[q] - 1 + ky) + off_h;
-              const float w_im = static_cast<float>(px[q] - 1 + kx) + off_w;
-              if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
-                const float hlf = floorf(h_im), wlf = floorf(w_im);
-                const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
-                const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf);
-                const int hh_i = hl + 1, wh_i = wl + 1;
-                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                const __half* xb = p.x + ibase + c0;
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                const bool tp = hl >= 0, bt = hh_i <= p.H - 1, lf = wl >= 0, rt = wh_i <= p.W - 1;
-                const uint4 v1 = (tp && lf) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hl * p.W + wl) * p.x_ld)) : z;
-                const uint4 v2 = (tp && rt) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hl * p.W + wh_i) * p.x_ld)) : z;
-                const uint4 v3 = (bt && lf) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hh_i * p.W + wl) * p.x_ld)) : z;
-                const uint4 v4 = (bt && rt) ? __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(hh_i * p.W + wh_i) * p.x_ld)) : z;
-                const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&v2);
-                const __half2* h3 = reinterpret_cast<const __half2*>(&v3);
-                const __half2* h4 = reinterpret_cast<const __half2*>(&v4);
-                __half2 o[4];
+            const __half2* h1 = reinterpret_cast<const __half2*>(&v[q][0]);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v[q][1]);
+            const __half2* h3 = reinterpret_cast<const __half2*>(&v[q][2]);
+            const __half2* h4 = reinterpret_cast<const __half2*>(&v[q][3]);
+            __half2 o2[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f1 = __half22float2(h1[e]), f2 = __half22float2(h2[e]);
-                  const float2 f3 = __half22float2(h3[e]), f4 = __half22float2(h4[e]);
-                  const float vx = (w1 * f1.x + w2 * f2.x + w3 * f3.x + w4 * f4.x) * mk;
-                  const float vy = (w1 * f1.y + w2 * f2.y + w3 * f3.y + w4 * f4.y) * mk;
-                  o[e] = __floats2half2_rn(vx, vy);
-                }
-                out = *reinterpret_cast<uint4*>(o);
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f1 = __half22float2(h1[e]), f2 = __half22float2(h2[e]);
+              const float2 f3 = __half22float2(h3[e]), f4 = __half22float2(h4[e]);
+              const float vx = wq[q].x * f1.x + wq[q].y * f2.x + wq[q].z * f3.x + wq[q].w * f4.x;
+              const float vy = wq[q].x * f1.y + wq[q].y * f2.y + wq[q].z * f3.y + wq[q].w * f4.y;
+              o2[e] = __floats2half2_rn(vx, vy);
             }
-            *reinterpret_cast<uint4*>(a_stage + sw128_off(r, j)) = out;
+            *reinterpret_cast<uint4*>(a_stage + sw128_off(r, j)) = *reinterpret_cast<uint4*>(o2);
           }
           fence_proxy_async();
-          mbar_arrive(&full_bar[s]);
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          c0 += BK;
+          if (c0 >= p.Cin) { c0 = 0; ++tap; }
         }
       }
     }
   } else if (warp == NPW) {
     // ================================================================ weight tiles by TMA
     if (lane == 0) {
-      int it = 0;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int n0 = (t % ntn) * BLOCK_N;
         int cw = 0, chh = 0, cn = 0;
@@ -420,18 +439,26 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           cw = ox * p.stride - p.pad;
           chh = oy * p.stride - p.pad;
         }
+        int tap = 0, c0 = 0, kx = 0, ky = 0;            // running (tap, channel) cursor: no divisions in the K loop
+        const int kc = A_TMA ? p.kc : BK, nbox = BK / kc, box_bytes = BM * kc * 2, ntap = p.kh * p.kw;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], A_TMA ? A_STAGE + B_STAGE : B_STAGE);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], A_TMA ? A_STAGE + B_STAGE : B_STAGE);
           if (A_TMA) {
-            const int k = kb * BK;
-            const int tap = k / p.Cin, c0 = k - tap * p.Cin;
-            const int ky = tap / p.kw, kx = tap - ky * p.kw;
-            tma_load_im2col_4d(smem_u32(a_smem + s * A_STAGE), &tmap_x, &full_bar[s], c0, cw, chh, cn,
-                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            const uint32_t a_dst = smem_u32(a_smem + stage * A_STAGE);
+            for (int jb = 0; jb < nbox; ++jb) {
+              const bool valid = tap < ntap;              // K tail: channel coordinate out of range -> TMA zero fill
+              tma_load_im2col_4d(a_dst + jb * box_bytes, &tmap_x, &full_bar[stage], valid ? c0 : p.Cin, cw, chh, cn,
+                                 static_cast<uint16_t>(valid ? kx : 0), static_cast<uint16_t>(valid ? ky : 0));
+              c0 += kc;
+              if (c0 >= p.Cin) {
+                c0 = 0; ++tap;
+                if (++kx == p.kw) { kx = 0; ++ky; }
+              }
+            }
           }
-          tma_load_2d(smem_u32(b_smem + s * B_STAGE), &tmap_w, &full_bar[s], kb * BK, n0);
+          tma_load_2d(smem_u32(b_smem + stage * B_STAGE), &tmap_w, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -439,24 +466,37 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     // ================================================================ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BLOCK_N);
-      int it = 0, ti = 0;
+      // Descriptors are "base + small delta": everything except the 14-bit start-address field is loop invariant, and
+      // the field is linear in the byte address, so the hot loop only does 64-bit adds (this single thread is the
+      // issue bottleneck of the whole CTA: keep its per-MMA instruction count minimal).
+      uint64_t a_d0[BK / 16];
+      const uint32_t a0 = smem_u32(a_smem), b0 = smem_u32(b_smem);
+#pragma unroll
+      for (int k4 = 0; k4 < BK / 16; ++k4) {
+        if (!A_TMA || p.kc == 64) a_d0[k4] = umma_desc_sw128(a0 + k4 * 32);
+        else if (p.kc == 32) a_d0[k4] = umma_desc_kmajor(a0 + (k4 >> 1) * (BM * 64) + (k4 & 1) * 32, 16, 512, 4);
+        else if (p.kc == 16) a_d0[k4] = umma_desc_kmajor(a0 + k4 * (BM * 32), 16, 256, 6);
+        else a_d0[k4] = umma_desc_kmajor(a0 + k4 * (2 * BM * 16), BM * 16, 128, 0);       // kc == 8: two boxes per MMA
+      }
+      const uint64_t b_d0 = umma_desc_sw128(b0);
+      int stage = 0, ti = 0;
+      uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
         const int acc = ti & 1;
         mbar_wait(&acc_empty[acc], ((ti >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_smem + s * A_STAGE);
-          const uint32_t b_addr = smem_u32(b_smem + s * B_STAGE);
+          const uint64_t a_off = static_cast<uint64_t>((stage * A_STAGE) >> 4);
+          const uint64_t b_off = static_cast<uint64_t>((stage * B_STAGE) >> 4);
 #pragma unroll
           for (int k4 = 0; k4 < BK / 16; ++k4) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k4 * 32), umma_desc_sw128(b_addr + k4 * 32), idesc,
-                     (kb | k4) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_d0[k4] + a_off, b_d0 + b_off + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);
       }
@@ -525,7 +565,7 @@ static int num_sms() {
 template <int BLOCK_N, int MODE, int NPW>
 static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx, const IgemmParams& p,
                        int use_tma_store, cudaStream_t st) {
-  using C = Cfg2<BLOCK_N>;
+  using C = Cfg2<BLOCK_N, MODE>;
   auto kern = igemm2_kernel<BLOCK_N, MODE, NPW>;
   static int attr_smem = 0;
   int smem = C::SMEM + g_tunable[MODE == MODE_DCN ? 0 : 1];
@@ -597,8 +637,12 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
   // A operand by im2col-mode TMA whenever a K block is one (tap, 64-channel) box
   CUtensorMap tx = tw;
   bool a_tma = false;
-  if (mode == MODE_CONV && p.Cin % 64 == 0 && g_tunable[4] == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
-      p.kw <= 16 && p.kh <= 16 && p.stride <= 8) {
+  IgemmParams pp = p;
+  const int kc = p.Cin % 64 == 0 ? 64 : p.Cin;
+  // im2col boxes narrower than 128 B are request-bound inside the TMA unit (measured: the 7x7 stem 1.8x slower than the
+  // cp.async gather), so they stay on the gather producers unless tunable 5 asks for them.
+  if (mode == MODE_CONV && (kc == 64 || ((kc == 32 || kc == 16 || kc == 8) && g_tunable[5] != 0)) && g_tunable[4] == 0 &&
+      (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.kw <= 16 && p.kh <= 16 && p.stride <= 8) {
     PFN_encodeIm2col enc2 = encode_im2col_fn();
     if (!enc2) return -1;
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
@@ -608,17 +652,21 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     int lower[2] = {-p.pad, -p.pad};
     int upper[2] = {p.pad - (p.kw - 1), p.pad - (p.kh - 1)};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(p.stride), static_cast<cuuint32_t>(p.stride), 1};
-    CUresult r = enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), gdim, gstr, lower, upper, 64, BM,
-                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d)", static_cast<int>(r)); return -1; }
+    const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : kc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), gdim, gstr, lower, upper,
+                      static_cast<cuuint32_t>(kc), BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d) kc=%d", static_cast<int>(r), kc); return -1; }
     a_tma = true;
+    pp.kc = kc;
   }
 #define MF_DISPATCH2(BN)                                                                          \
   if (bn == BN) {                                                                                 \
-    if (mode == MODE_DCN) return launch2_cfg<BN, MODE_DCN, 8>(tw, ty, tx, p, use_tma_store, st);  \
-    if (a_tma) return launch2_cfg<BN, MODE_CONV_TMA, 4>(tw, ty, tx, p, use_tma_store, st);        \
-    return launch2_cfg<BN, MODE_CONV, 4>(tw, ty, tx, p, use_tma_store, st);                       \
+    if (mode == MODE_DCN) return launch2_cfg<BN, MODE_DCN, 8>(tw, ty, tx, pp, use_tma_store, st);  \
+    if (a_tma) return launch2_cfg<BN, MODE_CONV_TMA, 4>(tw, ty, tx, pp, use_tma_store, st);        \
+    return launch2_cfg<BN, MODE_CONV, 4>(tw, ty, tx, pp, use_tma_store, st);                       \
   }
   MF_DISPATCH2(16)
   MF_DISPATCH2(32)

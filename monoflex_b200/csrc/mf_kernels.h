@@ -19,6 +19,7 @@ struct IgemmParams {
   int M;        // B*Ho*Wo
   int K_real;   // kh*kw*Cin
   int nkb;      // ceil(K_real / 64)
+  int kc;       // MODE_CONV_TMA: channels per im2col box (8/16/32/64), 64/kc taps per K block; 0 otherwise
   // DCN: per output pixel 18 offsets (dy,dx per tap) + 9 masks (already sigmoid-ed), fp32, row stride om_ld
   const float* offmask;
   int om_ld;

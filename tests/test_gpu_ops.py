@@ -28,6 +28,8 @@ CONV_CASES = [
     (3, 64, 7, 11, 64, 3, 1, 1, engine.ACT_RELU, True),        # tiles wrap across rows and images (im2col traversal)
     (2, 64, 17, 23, 128, 3, 2, 1, engine.ACT_RELU, False),     # stride 2 on odd sizes
     (2, 128, 5, 300, 64, 3, 1, 1, engine.ACT_NONE, False),     # wide rows: several 128-pixel tiles per image row
+    (2, 32, 12, 20, 64, 3, 2, 1, engine.ACT_RELU, False),      # Cin 32: 64-byte im2col boxes, 2 taps per K block
+    (1, 16, 33, 47, 32, 3, 1, 1, engine.ACT_RELU, True),       # Cin 16: 32-byte boxes, 4 taps per K block, ragged
 ]
 
 
