@@ -131,14 +131,14 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from monoflex_b200 import parallel
     from monoflex_b200 import synthetic as syn
     from monoflex_b200.config import default_cfg
     from monoflex_b200.model.detector import KeypointDetector
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init("nccl", dev)
     B = args.batch
     model = KeypointDetector(default_cfg(width=W, height=H))
     model.load_state_dict(syn.make_state_dict(0))
@@ -159,8 +159,7 @@ def main():
     launches_per_step = model.backbone.last_plan.n_launch + model.heads.predictor.last_plan.n_launch + 1 + 2
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident throughput
@@ -214,10 +213,7 @@ def main():
     barrier()
     if rank == 0:
         sampler.stop_flag = True
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], device=dev)
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
 
@@ -249,7 +245,7 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("head_conv_dram_bytes_per_launch")
         all_tf = sum(r["gflop"] for r in table) / total
-        roofline = {"bound": "tensor", "kernel": "igemm_kernel<128,CONV> head 3x3 64->2304 (+IABN epilogue)",
+        roofline = {"bound": "tensor", "kernel": "igemm2_kernel<128,CONV_TMA> head 3x3 64->2304 (+IABN epilogue)",
                     "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
                     "peak_source": "%s bf16 sustained (kernel timed inside the step; fp16 operands run at the bf16 rate)"
                                    % which,

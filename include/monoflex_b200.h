@@ -108,8 +108,14 @@ int mf_decode_detections(const float* heat, const float* reg, const float* calib
 int mf_dcn_v2_forward(const float* x, const float* w, const float* bias, const float* offset, const float* mask, float* y,
                       int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
                       int dw, int dg, void* workspace, size_t ws_bytes, void* stream);
-/* dcn_v2_backward (src/dcn_v2.h:48-59): training path, not built yet -> returns -2 */
-int mf_dcn_v2_backward(void);
+/* std::vector<at::Tensor>{dX,dOffset,dMask,dW,dB} dcn_v2_backward(input, weight, bias, offset, mask, grad_output, ...)
+ * (src/dcn_v2.h:48-59, dcn_v2_cuda.cu:206-335): fp32 NCHW, caller-allocated gradients (they are overwritten, not
+ * accumulated into). dX/dOffset/dMask use atomicAdd like the reference's col2im kernels (summation order not fixed).
+ * Compatibility path for `_DCNv2.backward` (autograd / gradcheck); the fused training kernels are a later row. */
+int mf_dcn_v2_backward(const float* x, const float* w, const float* bias, const float* offset, const float* mask,
+                       const float* grad_y, float* grad_x, float* grad_offset, float* grad_mask, float* grad_w,
+                       float* grad_bias, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
+                       int pw, int dh, int dw, int dg, void* workspace, size_t ws_bytes, void* stream);
 /* dcn_v2_psroi_pooling_forward/backward (src/dcn_v2.h:94-153): never instantiated by MonoFlex -> stubs returning -2 */
 int mf_dcn_v2_psroi_pooling_forward(void);
 int mf_dcn_v2_psroi_pooling_backward(void);

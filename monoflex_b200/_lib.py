@@ -33,7 +33,7 @@ SIGNATURES = {
     "mf_decode_detections": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                              _P, _P],
     "mf_dcn_v2_forward": [_P, _P, _P, _P, _P, _P] + [_I] * 14 + [_P, _SZ, _P],
-    "mf_dcn_v2_backward": [],
+    "mf_dcn_v2_backward": [_P] * 11 + [_I] * 14 + [_P, _SZ, _P],
     "mf_dcn_v2_psroi_pooling_forward": [],
     "mf_dcn_v2_psroi_pooling_backward": [],
 }

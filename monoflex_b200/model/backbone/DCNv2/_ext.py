@@ -40,8 +40,19 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
     return y
 
 
-def dcn_v2_backward(*args):
-    call("mf_dcn_v2_backward")
+def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                    dilation_h, dilation_w, deformable_group):
+    """-> (grad_input, grad_offset, grad_mask, grad_weight, grad_bias), src/dcn_v2.h:48-59."""
+    x, w, b = _check("input", input), _check("weight", weight), _check("bias", bias)
+    off, m, gy = _check("offset", offset), _check("mask", mask), _check("grad_output", grad_output)
+    B, C, H, W = x.shape
+    Co = w.shape[0]
+    gx, gw, gb = torch.empty_like(x), torch.empty_like(w), torch.empty_like(b)
+    go, gm = torch.empty_like(off), torch.empty_like(m)
+    call("mf_dcn_v2_backward", x.data_ptr(), w.data_ptr(), b.data_ptr(), off.data_ptr(), m.data_ptr(), gy.data_ptr(),
+         gx.data_ptr(), go.data_ptr(), gm.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, C, H, W, Co, kernel_h, kernel_w,
+         stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, None, 0, stream())
+    return gx, go, gm, gw, gb
 
 
 def dcn_v2_psroi_pooling_forward(*args):

@@ -256,8 +256,11 @@ class DLASeg(nn.Module):
             raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only (input is on %s); no CPU fallback" % x.device)
         x = x.float().contiguous()
         plan = self._plan_for(x)
+        self.run_plan(plan, x)
+        return plan.output.nchw_view()
+
+    def run_plan(self, plan, x):
         B, C, H, W = x.shape
         call("mf_pack_image", x.data_ptr(), plan.input.ptr(), B, C, H, W, stream())
         plan.run()
         self.last_plan = plan
-        return plan.output.nchw_view()

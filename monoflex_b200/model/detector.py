@@ -1,7 +1,16 @@
 """KeypointDetector (reference: model/detector.py:11-37): backbone -> heads, same constructor and forward signature so
-engine/trainer.py:109 and engine/inference.py:38 call it unchanged."""
+engine/trainer.py:109 and engine/inference.py:38 call it unchanged.
+
+Eval forwards are replayed from a CUDA graph: shapes are static (384x1280 zero-padded images), so the
+~135 kernel launches of a forward are captured once per (input shape, parameter version) and replayed with one
+cudaGraphLaunch; per call only the image batch and the per-image target fields are copied into static buffers.
+`MF_CUDA_GRAPH=0` (or `model.use_cuda_graph = False`) runs the same launches eagerly."""
+import os
+
+import torch
 from torch import nn
 
+from .. import engine
 from ..structures import to_image_list
 from .backbone import build_backbone
 from .head.detector_head import bulid_head
@@ -13,12 +22,57 @@ class KeypointDetector(nn.Module):
         self.backbone = build_backbone(cfg)
         self.heads = bulid_head(cfg, self.backbone.out_channels)
         self.test = cfg.DATASETS.TEST_SPLIT == 'test'
+        self.use_cuda_graph = os.environ.get("MF_CUDA_GRAPH", "1") != "0"
+        self._graph = None
 
     def forward(self, images, targets=None):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         images = to_image_list(images)
-        features = self.backbone(images.tensors)
         if self.training:
+            features = self.backbone(images.tensors)
             return self.heads(features, targets)
-        return self.heads(features, targets, test=self.test)
+        x = images.tensors
+        if not self.use_cuda_graph or not x.is_cuda:
+            features = self.backbone(x)
+            return self.heads(features, targets, test=self.test)
+        return self._forward_graph(x, targets)
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def _forward_graph(self, x, targets):
+        pred, post = self.heads.predictor, self.heads.post_processor
+        post.check_config()
+        x = x.float().contiguous()
+        k_edge = targets[0].get_field("edge_indices").shape[0]
+        key = (tuple(x.shape), x.device, k_edge, engine.fingerprint(self), post.det_threshold, post.max_detection)
+        g = self._graph
+        if g is None or g['key'] != key:
+            g = self._capture(x, targets, key)
+        g['x'].copy_(x, non_blocking=True)
+        pred.load_targets(g['plan_h'], targets)
+        meta = post.prepare_targets(targets, self.test, x.device)
+        for dst, src in zip(g['meta'], meta):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g['graph'].replay()
+        return post.finish(g['ws'], g['plan_h'].cls)
+
+    def _capture(self, x, targets, key):
+        pred, post = self.heads.predictor, self.heads.post_processor
+        xs = x.clone()
+        plan_b = self.backbone._plan_for(xs)
+        plan_h = pred.plan_for(plan_b.output.nchw_view(), key[2])
+        pred.load_targets(plan_h, targets)
+        meta = tuple(t.clone() for t in post.prepare_targets(targets, self.test, x.device))
+
+        def body():
+            self.backbone.run_plan(plan_b, xs)
+            plan_h.run()
+            return post.launch(plan_h.cls, plan_h.reg, meta)
+        body()                                   # eager warm-up: func attributes, tensor-map driver entry points, workspaces
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ws = body()
+        self._graph = {'key': key, 'graph': graph, 'x': xs, 'plan_b': plan_b, 'plan_h': plan_h, 'meta': meta, 'ws': ws}
+        return self._graph

@@ -57,29 +57,28 @@ class PostProcessor(nn.Module):
         self._meta_cache = (key, out, targets)
         return out
 
-    def forward(self, predictions, targets, features=None, test=False, refine_module=None):
-        if self.output_depth != 'soft':
-            raise NotImplementedError("only OUTPUT_DEPTH='soft' (runs/monoflex.yaml) is built")
-        if self.eval_dis_iou or self.eval_depth:
-            raise NotImplementedError("--eval_iou / --eval_depth diagnostics are out of scope")
-        heat, reg = predictions['cls'], predictions['reg']
-        if not heat.is_cuda:
-            raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
-        heat, reg = heat.float().contiguous(), reg.float().contiguous()
-        B = heat.shape[0]
-        calib, pad, size = self.prepare_targets(targets, test, heat.device)
-        K = self.max_detection
+    def launch(self, heat, reg, meta):
+        """the two decode kernels (asynchronous; no host sync)"""
+        calib, pad, size = meta
+        B, K = heat.shape[0], self.max_detection
         if self._ws is None or (self._ws.B, self._ws.C) != (B, heat.shape[1]) or self._ws.scores.device != heat.device:
             self._ws = DecodeWorkspace(B, heat.shape[1], K, reg.shape[1], heat.device)
-        ws = decode_detections(heat, reg, calib, pad, size, self.dim_mean, K, self.det_threshold, False, self._ws)
+        return decode_detections(heat, reg, calib, pad, size, self.dim_mean, K, self.det_threshold, False, self._ws)
+
+    def finish(self, ws, heat):
+        """host side: read the valid counts (the reference syncs at `valid_mask.sum() == 0`, :106) and slice."""
+        B = heat.shape[0]
         visualize_preds = {'heat_map': heat}
-        counts = ws.count.tolist()            # host sync, like `valid_mask.sum() == 0` in the reference (:106)
+        counts = ws.count.tolist()
         if B == 1:
             n = counts[0]
             result = ws.result[0, :n]
             vis_scores = ws.scores[0, :n]
             pois = ws.pois[0, :n]
             batch_idxs = torch.zeros(n, dtype=torch.long, device=heat.device)
+        elif all(n == ws.K for n in counts):
+            result, vis_scores, pois = ws.result.view(-1, 14), ws.scores.view(-1), ws.pois.view(-1, ws.R)
+            batch_idxs = torch.arange(B, device=heat.device).repeat_interleave(ws.K)
         else:
             rows = [ws.result[b, :n] for b, n in enumerate(counts)]
             result = torch.cat(rows, 0)
@@ -87,9 +86,26 @@ class PostProcessor(nn.Module):
             pois = torch.cat([ws.pois[b, :n] for b, n in enumerate(counts)], 0)
             batch_idxs = torch.cat([torch.full((n,), b, dtype=torch.long, device=heat.device)
                                     for b, n in enumerate(counts)], 0)
+        # detections are tiny: hand out copies, not views of the (re-used) decode workspace
+        result, vis_scores, pois = result.clone(), vis_scores.clone(), pois.clone()
         visualize_preds['keypoints'] = pois[:, self.key2channel('corner_offset')].reshape(-1, 10, 2)
         conf = result[:, 13] / vis_scores.clamp_min(1e-12) if result.shape[0] else result.new_zeros(0)
         eval_utils = {'dis_ious': None, 'depth_errors': None, 'uncertainty_conf': conf,
                       'estimated_depth_error': None, 'vis_scores': vis_scores, 'batch_idxs': batch_idxs,
                       'counts': counts, 'topk': (ws.scores, ws.inds, ws.clses, ws.ys, ws.xs), 'padded_result': ws.result}
         return result, eval_utils, visualize_preds
+
+    def check_config(self):
+        if self.output_depth != 'soft':
+            raise NotImplementedError("only OUTPUT_DEPTH='soft' (runs/monoflex.yaml) is built")
+        if self.eval_dis_iou or self.eval_depth:
+            raise NotImplementedError("--eval_iou / --eval_depth diagnostics are out of scope")
+
+    def forward(self, predictions, targets, features=None, test=False, refine_module=None):
+        self.check_config()
+        heat, reg = predictions['cls'], predictions['reg']
+        if not heat.is_cuda:
+            raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
+        heat, reg = heat.float().contiguous(), reg.float().contiguous()
+        ws = self.launch(heat, reg, self.prepare_targets(targets, test, heat.device))
+        return self.finish(ws, heat)

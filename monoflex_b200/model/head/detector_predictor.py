@@ -135,23 +135,29 @@ class _predictor(nn.Module):
         P.cls, P.reg, P.hidden = cls, reg, hid
         return P
 
-    def forward(self, features, targets):
-        if self.training:
-            raise NotImplementedError("training path not built yet (no PyTorch fallback)")
+    def plan_for(self, features, K_edge):
         feat = _as_rows(features)
-        edge_indices = torch.stack([t.get_field("edge_indices") for t in targets])      # B x K x 2   (:138)
-        edge_lens = torch.stack([t.get_field("edge_len") for t in targets]).view(-1)    # B           (:139)
-        K_edge = edge_indices.shape[1]
         key = (feat.buf.data_ptr(), feat.ch_off, feat.B, feat.H, feat.W, feat.buf.shape[1], K_edge,
                engine.fingerprint(self))
         plan = self._plans.get('plan')
         if plan is None or self._plans.get('key') != key:
             plan = self.build_plan(feat, K_edge)
             self._plans = {'plan': plan, 'key': key}
-        plan.edge_idx.copy_(edge_indices, non_blocking=True)
-        plan.edge_len.copy_(edge_lens, non_blocking=True)
-        plan.run()
         self.last_plan = plan
+        return plan
+
+    @staticmethod
+    def load_targets(plan, targets):
+        """edge_indices [B,K,2] / edge_len [B] of the batch into the plan's static device buffers (:138-139)."""
+        plan.edge_idx.copy_(torch.stack([t.get_field("edge_indices") for t in targets]), non_blocking=True)
+        plan.edge_len.copy_(torch.stack([t.get_field("edge_len") for t in targets]).view(-1), non_blocking=True)
+
+    def forward(self, features, targets):
+        if self.training:
+            raise NotImplementedError("training path not built yet (no PyTorch fallback)")
+        plan = self.plan_for(features, targets[0].get_field("edge_indices").shape[0])
+        self.load_targets(plan, targets)
+        plan.run()
         return {'cls': plan.cls, 'reg': plan.reg}
 
 

@@ -114,7 +114,7 @@ def test_batch_and_full_resolution():
         cls3 = m.heads.predictor.last_plan.cls
         assert torch.equal(cls3[0], cls1[0]) and torch.equal(cls3[1], cls1[7])   # images are independent
         assert eu1['counts'] == [50] * B and r1.shape == (50 * B, 14)
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
         taps = {}
         mo.detector_eval(sd, x[:1], tg['edge_indices'][:1], tg['edge_len'][:1], tg['calib_P'][:1], tg['pad_size'][:1],
                          tg['size'][:1], 0.0, taps)

@@ -166,6 +166,39 @@ def test_ext_dcn_v2_forward_fp32_golden_and_kat():
         _ext.dcn_v2_psroi_pooling_forward()
 
 
+def test_ext_dcn_v2_backward_vs_oracle_autograd_and_gradcheck():
+    """Boundary B backward (src/dcn_v2.h:48-59): gradients vs torch autograd through the CPU oracle, then the reference's
+    own gradcheck recipe (testcuda.py:69-97: eps 1e-3, atol 1e-4, rtol 1e-2, fp32)."""
+    from monoflex_b200.model.backbone.DCNv2 import _ext
+    from monoflex_b200.model.backbone.DCNv2.dcn_v2 import dcn_v2_conv
+    gen = np.random.Generator(np.random.PCG64(31))
+    B, C, H, W, Co = 2, 6, 7, 9, 5
+    x = torch.from_numpy(gen.standard_normal((B, C, H, W)).astype(np.float32))
+    off = torch.from_numpy((gen.standard_normal((B, 18, H, W)) * 1.3).astype(np.float32))
+    mask = torch.from_numpy(gen.uniform(0.1, 0.9, (B, 9, H, W)).astype(np.float32))
+    w = torch.from_numpy((gen.standard_normal((Co, C, 3, 3)) * 0.3).astype(np.float32))
+    bias = torch.from_numpy(gen.standard_normal(Co).astype(np.float32))
+    gy = torch.from_numpy(gen.standard_normal((B, Co, H, W)).astype(np.float32))
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, bias, off, mask)]
+    mo.dcn_v2_forward(*leaves).backward(gy)
+    ref = [t.grad for t in leaves]                      # dX, dW, dB, dOff, dMask
+    gx, go, gm, gw, gb = _ext.dcn_v2_backward(x.cuda(), w.cuda(), bias.cuda(), off.cuda(), mask.cuda(), gy.cuda(),
+                                              3, 3, 1, 1, 1, 1, 1, 1, 1)
+    for name, got, want in (("dX", gx, ref[0]), ("dW", gw, ref[1]), ("dB", gb, ref[2]), ("dOff", go, ref[3]),
+                            ("dMask", gm, ref[4])):
+        assert rel_err(got.cpu(), want) < 1e-4, name
+    # autograd.Function end to end + the reference's gradcheck recipe
+    N, inC, inH, inW, outC = 2, 2, 4, 4, 2
+    torch.manual_seed(0)
+    inp = (torch.rand(N, inC, inH, inW, device="cuda") * 0.01).requires_grad_(True)
+    offset = (torch.randn(N, 18, inH, inW, device="cuda") * 2).requires_grad_(True)
+    msk = torch.sigmoid(torch.rand(N, 9, inH, inW, device="cuda")).detach().requires_grad_(True)
+    weight = torch.randn(outC, inC, 3, 3, device="cuda").requires_grad_(True)
+    b2 = torch.rand(outC, device="cuda").requires_grad_(True)
+    assert torch.autograd.gradcheck(dcn_v2_conv, (inp, offset, msk, weight, b2, 1, 1, 1, 1), eps=1e-3, atol=1e-4,
+                                    rtol=1e-2, nondet_tol=1e-5)
+
+
 def test_maxpool_and_upsample_add():
     gen = np.random.Generator(np.random.PCG64(7))
     x = h16(torch.from_numpy(gen.standard_normal((2, 64, 12, 20)).astype(np.float32)))

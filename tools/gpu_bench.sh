@@ -23,7 +23,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 echo "ncu list rc $?"
 fi
 if [ -n "$NCU_FULL" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o /tmp/prof_$R python tools/profile_kernels.py > gpurun_out/ncu_full_$R.log 2>&1
+timeout 600 ncu --set full --kernel-name regex:"igemm|nms_|topk_" --clock-control none --import-source on --profile-from-start off -f -o /tmp/prof_$R python tools/profile_kernels.py > gpurun_out/ncu_full_$R.log 2>&1
 echo "ncu full rc $?"; tail -3 gpurun_out/ncu_full_$R.log
 ncu -i /tmp/prof_$R.ncu-rep --page raw --csv > gpurun_out/prof_raw_$R.csv 2>/dev/null
 ncu -i /tmp/prof_$R.ncu-rep --page details --csv > gpurun_out/prof_details_$R.csv 2>/dev/null
