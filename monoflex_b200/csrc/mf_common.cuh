@@ -54,6 +54,10 @@ MF_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta
 MF_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+// same, allocating in L1 (.ca): the gather of small-Cin layers re-reads every input pixel kh*kw times from the same CTA
+MF_DEVINL void cp_async16_ca(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 MF_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 MF_DEVINL void cp_async_wait() {

@@ -25,16 +25,20 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE = BM * BK * 2;   // 16 KB
 
+static constexpr int AS_MAX_KB = 9;          // A-stationary mode: at most 9 resident K blocks (3x3 taps of 64 channels)
+
 template <int BLOCK_N, int MODE>
 struct Cfg2 {
-  static constexpr int STAGES = MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : 4));
-  static constexpr int LAG = BLOCK_N >= 64 ? 3 : 2;            // cp.async groups in flight per producer thread
+  static constexpr bool A_STAT = MODE == MODE_CONV_TMA_AS;
+  static constexpr int STAGES = A_STAT ? 3 : (MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : (BLOCK_N >= 32 ? 5 : 6))));
+  static constexpr int A_REGION = (A_STAT ? AS_MAX_KB : STAGES) * A_STAGE;
+  static constexpr int LAG = BLOCK_N >= 64 ? 3 : (BLOCK_N >= 32 ? 3 : 4);   // cp.async groups in flight per producer thread
   static constexpr int CTAS_PER_SM = BLOCK_N >= 64 ? 1 : 2;
   static constexpr int B_STAGE = BLOCK_N * BK * 2;
   static constexpr int OUT_STAGE = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;
-  static constexpr int BAR_BYTES = 1024;                        // barriers + tmem ptr + scale/shift staging
+  static constexpr int BAR_BYTES = 256;                         // barriers + tmem ptr
   static constexpr int PRM_BYTES = MODE == MODE_DCN ? 9 * BM * 32 : 0;   // DCN sampling records
-  static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + PRM_BYTES + 1024;
+  static constexpr int SMEM = A_REGION + STAGES * B_STAGE + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + PRM_BYTES + 1024;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;                // power of two >= 32 for every BLOCK_N used
@@ -85,7 +89,8 @@ template <int BLOCK_N, int MODE, int NPW>
 __global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE>::CTAS_PER_SM)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
               const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
-  constexpr bool A_TMA = (MODE == MODE_CONV_TMA);
+  constexpr bool A_TMA = (MODE == MODE_CONV_TMA || MODE == MODE_CONV_TMA_AS);
+  constexpr bool A_STAT = (MODE == MODE_CONV_TMA_AS);   // A tile of an m-tile stays resident while all n-tiles stream B
   constexpr int EPI_THREADS = A_TMA ? 128 + NPW * 32 : 128;
   using C = Cfg2<BLOCK_N, MODE>;
   constexpr int STAGES = C::STAGES;
@@ -98,13 +103,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + STAGES * A_STAGE;
+  uint8_t* b_smem = smem + C::A_REGION;
   uint8_t* o_smem = b_smem + STAGES * B_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(o_smem + C::OUT_STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_full = acc_empty + 2;            // [AS_MAX_KB]  (A-stationary mode)
+  uint64_t* a_empty = a_full + AS_MAX_KB;      // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 1);
   float* sc_s = reinterpret_cast<float*>(o_smem + C::OUT_STAGE + C::BAR_BYTES);
   float* sh_s = sc_s + BLOCK_N;
   uint8_t* prm_smem = reinterpret_cast<uint8_t*>(sh_s + BLOCK_N);      // MODE_DCN only: 9*128 sampling records (36 KB)
@@ -116,6 +123,12 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   const int ntm = MODE == MODE_DCN ? p.B * tiles_x * tiles_y : (p.M + BM - 1) / BM;
   const int ntiles = ntn * ntm;
   const int nkb = p.nkb;
+  // tile enumeration: plain = tile t, t += grid (n fastest); A-stationary = m-tile outer (strided over CTAs), n inner
+  const int n_outer = A_STAT ? ntm : ntiles, n_inner = A_STAT ? ntn : 1;
+#define MF_TILE_LOOP                                                         \
+  for (int outer = blockIdx.x; outer < n_outer; outer += gridDim.x)          \
+    for (int inner = 0; inner < n_inner; ++inner)
+#define MF_TILE_INDEX (A_STAT ? outer * ntn + inner : outer)
   const int HoWo = p.Ho * p.Wo;
 
   if (warp == NPW && lane == 0) {
@@ -130,6 +143,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], EPI_THREADS);
     }
+    for (int a = 0; a < AS_MAX_KB; ++a) mbar_init(&a_full[a], 1);
+    mbar_init(a_empty, 1);
     fence_mbar_init();
   }
   if (warp == NPW + 1) tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
@@ -146,8 +161,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     constexpr int NCHUNK = BLOCK_N / CHUNK;
     constexpr int NGROUPS = EPI_THREADS / 128;
     const bool staged = use_tma_store != 0;             // host guarantees OUT_F16_NHWC && BLOCK_N >= 64
-    int ti = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+    int ti = -1;
+    MF_TILE_LOOP {
+      ++ti;
+      const int t = MF_TILE_INDEX;
       const int acc = ti & 1;
       const int n0 = (t % ntn) * BLOCK_N;
       const int m_tile = t / ntn;
@@ -322,7 +339,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             const int iy = iy0[q] + ky, ix = ix0[q] + kx;
             const bool ok = kvalid && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
             const __half* src = ok ? p.x + base[q] + koff : p.x;
-            cp_async16(a_stage + sw128_off(r, j), src, ok ? 16u : 0u);
+            cp_async16_ca(a_stage + sw128_off(r, j), src, ok ? 16u : 0u);
           }
           cp_async_commit();
           if (it >= LAG) {
@@ -426,12 +443,14 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   } else if (warp == NPW) {
     // ================================================================ weight tiles by TMA
     if (lane == 0) {
-      int it = 0, stage = 0;
+      int stage = 0, mi = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int kc = A_TMA ? p.kc : BK, nbox = BK / kc, box_bytes = BM * kc * 2, ntap = p.kh * p.kw;
+      MF_TILE_LOOP {
+        const int t = MF_TILE_INDEX;
         const int n0 = (t % ntn) * BLOCK_N;
         int cw = 0, chh = 0, cn = 0;
-        if (A_TMA) {                      // coordinates of the tile's first output pixel in input space (incl. -pad)
+        if (A_TMA && (!A_STAT || inner == 0)) {   // coordinates of the tile's first output pixel in input space (incl. -pad)
           const int m0 = (t / ntn) * BM;
           cn = m0 / HoWo;
           const int rem = m0 - cn * HoWo;
@@ -439,12 +458,23 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           cw = ox * p.stride - p.pad;
           chh = oy * p.stride - p.pad;
         }
+        if (A_STAT && inner == 0) {               // the whole A tile (all taps) once per m-tile, one barrier per K block
+          mbar_wait(a_empty, (mi & 1) ^ 1);
+          ++mi;
+          int tap = 0, c0 = 0, kx = 0, ky = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_arrive_expect_tx(&a_full[kb], A_STAGE);
+            tma_load_im2col_4d(smem_u32(a_smem + kb * A_STAGE), &tmap_x, &a_full[kb], c0, cw, chh, cn,
+                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            c0 += BK;
+            if (c0 >= p.Cin) { c0 = 0; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
+          }
+        }
         int tap = 0, c0 = 0, kx = 0, ky = 0;            // running (tap, channel) cursor: no divisions in the K loop
-        const int kc = A_TMA ? p.kc : BK, nbox = BK / kc, box_bytes = BM * kc * 2, ntap = p.kh * p.kw;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_TMA ? A_STAGE + B_STAGE : B_STAGE);
-          if (A_TMA) {
+          mbar_arrive_expect_tx(&full_bar[stage], (A_TMA && !A_STAT) ? A_STAGE + B_STAGE : B_STAGE);
+          if (A_TMA && !A_STAT) {
             const uint32_t a_dst = smem_u32(a_smem + stage * A_STAGE);
             for (int jb = 0; jb < nbox; ++jb) {
               const bool valid = tap < ntap;              // K tail: channel coordinate out of range -> TMA zero fill
@@ -479,17 +509,20 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         else a_d0[k4] = umma_desc_kmajor(a0 + k4 * (2 * BM * 16), BM * 16, 128, 0);       // kc == 8: two boxes per MMA
       }
       const uint64_t b_d0 = umma_desc_sw128(b0);
-      int stage = 0, ti = 0;
+      int stage = 0, ti = -1, mi = -1;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ti) {
+      MF_TILE_LOOP {
+        ++ti;
+        if (inner == 0) ++mi;
         const int acc = ti & 1;
         mbar_wait(&acc_empty[acc], ((ti >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
         for (int kb = 0; kb < nkb; ++kb) {
+          if (A_STAT && inner == 0) mbar_wait(&a_full[kb], mi & 1);   // resident A block of this m-tile has landed
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_off = static_cast<uint64_t>((stage * A_STAGE) >> 4);
+          const uint64_t a_off = static_cast<uint64_t>(((A_STAT ? kb : stage) * A_STAGE) >> 4);
           const uint64_t b_off = static_cast<uint64_t>((stage * B_STAGE) >> 4);
 #pragma unroll
           for (int k4 = 0; k4 < BK / 16; ++k4) {
@@ -499,6 +532,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);
+        if (A_STAT && inner == n_inner - 1) umma_commit(a_empty);   // every MMA reading the resident A tile is done
       }
     }
     __syncwarp();
@@ -662,12 +696,17 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     a_tma = true;
     pp.kc = kc;
   }
+  const int ntn_host = (p.Cout + bn - 1) / bn;
 #define MF_DISPATCH2(BN)                                                                          \
   if (bn == BN) {                                                                                 \
     if (mode == MODE_DCN) return launch2_cfg<BN, MODE_DCN, 8>(tw, ty, tx, pp, use_tma_store, st);  \
+    if (a_tma && BN == 128 && pp.kc == 64 && pp.nkb <= AS_MAX_KB && ntn_host >= 4 && g_tunable[6] == 1)      \
+      return launch2_cfg<128, MODE_CONV_TMA_AS, 4>(tw, ty, tx, pp, use_tma_store, st);             \
     if (a_tma) return launch2_cfg<BN, MODE_CONV_TMA, 4>(tw, ty, tx, pp, use_tma_store, st);        \
     return launch2_cfg<BN, MODE_CONV, 4>(tw, ty, tx, pp, use_tma_store, st);                       \
   }
+  if (mode == MODE_DCN && g_tunable[7] != 2 && bn == 64) return launch2_cfg<64, MODE_DCN, 16>(tw, ty, tx, pp, use_tma_store, st);
+  if (mode == MODE_DCN && g_tunable[7] != 2 && bn == 128) return launch2_cfg<128, MODE_DCN, 16>(tw, ty, tx, pp, use_tma_store, st);
   MF_DISPATCH2(16)
   MF_DISPATCH2(32)
   MF_DISPATCH2(64)
