@@ -57,6 +57,15 @@ int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, co
                        int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift,
                        const void* res, int res_ld, int act, int out_mode, void* y, int y_ld, void* stream);
 
+/* Full-resolution stem convolutions (DLA base_layer 7x7 3->16, level0 3x3 16->16, level1 3x3/2 16->32,
+ * dla_dcn.py:268-282) on "planar" tensors [B][H][G][W/npar][8] fp16 (G = Cin/8 channel planes x npar column parities):
+ * every input row segment is loaded once by TMA and the taps are read through shifted no-swizzle UMMA descriptors, no
+ * im2col copies. Cin in {8, 16}; stride 1 (in_npar 1) or 2 (in_npar 2, 3x3, pad 1). Cin = 8 weights are packed with kw
+ * padded to 8. Output: planar for the next stem layer (out_planar = 1, out_npar 1 or 2) or NHWC rows (y_ld). */
+int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar, const void* w_packed, int n_pad, int k_pad,
+                       int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
+                       int out_planar, int out_npar, void* y, int y_ld, void* stream);
+
 /* Fused DCNv2 (3x3, stride 1, pad 1, dilation 1, deformable_groups 1): bilinear gather of the modulated columns straight
  * into the MMA operand tile, contraction with the packed weights, affine (+bias, BN) and activation epilogue.
  * Replaces _ext.dcn_v2_forward + BatchNorm2d + ReLU of DeformConv (dla_dcn.py:384-396; src/cuda/dcn_v2_cuda.cu:42-172,

@@ -264,7 +264,7 @@ int mf_set_conv_impl(int impl) {
 }
 int mf_conv_block_n(int cout) { return igemm_block_n(cout); }
 int mf_set_tunable(int id, int value) {
-  if (id < 0 || id >= 8) { set_error("mf_set_tunable: id out of range"); return -1; }
+  if (id < 0 || id >= 16) { set_error("mf_set_tunable: id out of range"); return -1; }
   g_tunable[id] = value;
   return 0;
 }
@@ -291,6 +291,14 @@ int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, co
   p.res = static_cast<const __half*>(res); p.res_ld = res_ld; p.act = act; p.out_mode = out_mode; p.y = y; p.y_ld = y_ld;
   if (p.Ho <= 0 || p.Wo <= 0 || Cout <= 0) { set_error("mf_conv2d_nhwc_f16: empty output"); return -1; }
   return run_gemm(p, w_packed, n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
+}
+
+int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar, const void* w_packed, int n_pad, int k_pad,
+                       int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
+                       int out_planar, int out_npar, void* y, int y_ld, void* stream) {
+  return launch_rows_conv(static_cast<const __half*>(x), B, H, W, Cin, in_npar, static_cast<const __half*>(w_packed), n_pad,
+                          k_pad, kh, kw, stride, pad, Cout, scale, shift, act, out_planar, out_npar, static_cast<__half*>(y),
+                          y_ld, MF_STREAM(stream));
 }
 
 int mf_dcn_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const float* offmask, int om_ld,

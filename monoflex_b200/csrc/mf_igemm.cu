@@ -335,7 +335,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int g_tunable[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] extra dynamic smem (bytes) for DCN CTAs, [1] same for conv CTAs
+int g_tunable[16] = {0};   // [0] extra dynamic smem (bytes) for DCN CTAs, [1] same for conv CTAs
 
 template <int BLOCK_N, int MODE, int NPW>
 static int launch_cfg(const CUtensorMap& tm, const IgemmParams& p, cudaStream_t st) {

@@ -35,10 +35,13 @@ struct IgemmParams {
   int y_ld;
 };
 
-extern int g_tunable[8];
+extern int g_tunable[16];
 int igemm_block_n(int cout);
 int launch_igemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
+int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar, const __half* wp, int n_pad, int k_pad,
+                     int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
+                     int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st);
 int launch_simt_gemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 
 }  // namespace mf

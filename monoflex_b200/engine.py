@@ -26,6 +26,7 @@ class Act(object):
         self.buf = None      # torch.half tensor [B*H*W, ld]
         self.owner = None    # concat group this activation is a slice of
         self.ch_off = 0
+        self.npar = 0        # > 0: planar stem layout with `npar` column parities (16-byte pixels)
 
     @property
     def M(self):
@@ -39,7 +40,12 @@ class Act(object):
         return self.buf.data_ptr() + 2 * self.ch_off
 
     def nchw_view(self):
-        """zero-copy torch view [B,C,H,W] (channels-last strides) of this activation."""
+        """torch view [B,C,H,W] of this activation (zero-copy, channels-last strides, for NHWC rows; a reshaped copy for
+        the planar stem layout [B][H][C/8 x npar][W/npar][8])."""
+        if self.npar:
+            P, Wg = self.C // 8, self.W // self.npar
+            v = self.buf.view(self.B, self.H, P, self.npar, Wg, 8).permute(0, 2, 5, 1, 4, 3)
+            return v.reshape(self.B, self.C, self.H, self.W)
         return self.buf.view(self.B, self.H, self.W, -1)[..., self.ch_off:self.ch_off + self.C].permute(0, 3, 1, 2)
 
 
@@ -77,7 +83,10 @@ class Plan(object):
     def finalize(self):
         for a in self.acts:
             if a.owner is None:
-                a.buf = torch.empty(a.M, a.C, dtype=torch.half, device=self.device)
+                if a.npar:
+                    a.buf = torch.empty(a.M * a.C // 8, 8, dtype=torch.half, device=self.device)
+                else:
+                    a.buf = torch.empty(a.M, a.C, dtype=torch.half, device=self.device)
         for a in self.acts:
             if a.owner is not None:
                 root, off = a, 0
@@ -187,6 +196,29 @@ class Plan(object):
         self.add("mf_dcn_nhwc_f16", lambda: (
             x.ptr(), x.ld, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
             shift.data_ptr(), ACT_RELU, OUT_F16_NHWC, y.ptr(), y.ld))
+        return y
+
+    def planar_act(self, B, H, W, C, npar):
+        a = self.act(B, H, W, C)
+        a.npar = npar
+        return a
+
+    def conv_rows(self, x, weight, stride, pad, bn, out_planar, out_npar=1):
+        """Stem convolution on 16-byte-pixel planes (csrc/mf_rows.cu): x is the packed image (8 ch) or a planar
+        16-channel activation; output planar (next stem layer) or NHWC rows."""
+        cout, cin_w, kh, kw = weight.shape
+        cin = x.C
+        in_npar = x.npar if x.npar else 1
+        w = weight.detach().float()
+        if cin == 8:
+            w = torch.nn.functional.pad(w, (0, 8 - kw, 0, 0, 0, 8 - cin_w))     # kw -> 8 taps, 3 -> 8 channels
+        wp, n_pad, k_pad = self.pack_weight(w.contiguous(), cin_pad=cin)
+        scale, shift = self.affine(cout, n_pad, bn)
+        Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1
+        y = self.planar_act(x.B, Ho, Wo, cout, out_npar) if out_planar else self.act(x.B, Ho, Wo, cout)
+        self.add("mf_conv2d_rows_f16", lambda: (
+            x.ptr(), x.B, x.H, x.W, cin, in_npar, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout, scale.data_ptr(),
+            shift.data_ptr(), ACT_RELU, 1 if out_planar else 0, out_npar, y.ptr(), y.ld if not out_planar else 8))
         return y
 
     def maxpool2(self, x, out=None):

@@ -127,12 +127,23 @@ class DLA(nn.Module):
 
     def plan(self, P, x8):
         """DLA.forward (:324-331). x8: image already packed to NHWC fp16 with 8 channels (3 real + 5 zero)."""
-        x = P.conv(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], cin_pad=8)
+        import os
+        rows_ok = (len(self.level0) == 3 and len(self.level1) == 3 and self.channels[0] == 16 and x8.W % 2 == 0 and
+                   self.level1[0].stride[0] == 2 and os.environ.get("MF_NO_ROWS_STEM", "0") != "1")
         y = []
-        for seq in (self.level0, self.level1):
-            for i in range(0, len(seq), 3):
-                x = P.conv(x, seq[i].weight, seq[i].stride[0], 1, seq[i + 1])
-            y.append(x)
+        if rows_ok:
+            # full-resolution stem on 16-byte-pixel planes: no im2col copies (csrc/mf_rows.cu)
+            x8.npar = 1
+            a0 = P.conv_rows(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], out_planar=True, out_npar=1)
+            a1 = P.conv_rows(a0, self.level0[0].weight, 1, 1, self.level0[1], out_planar=True, out_npar=2)
+            x = P.conv_rows(a1, self.level1[0].weight, 2, 1, self.level1[1], out_planar=False)
+            y += [a1, x]
+        else:
+            x = P.conv(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], cin_pad=8)
+            for seq in (self.level0, self.level1):
+                for i in range(0, len(seq), 3):
+                    x = P.conv(x, seq[i].weight, seq[i].stride[0], 1, seq[i + 1])
+                y.append(x)
         for i in range(2, 6):
             x = getattr(self, 'level%d' % i).plan(P, x)
             y.append(x)
