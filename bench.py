@@ -107,7 +107,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = cpu_threads()
-    config = {"workload": "DLA-34+DCNv2+heads inference, batch %d/GPU, 384x1280 synthetic, %dxB200 (BASELINE configs[1])"
+    config = {"workload": "DLA-34+DCNv2+heads+decode inference, batch %d/GPU, 384x1280 synthetic, %dxB200 (BASELINE configs[1]; --batch 32 = configs[3])"
               % (args.batch, args.gpus), "batch_per_gpu": args.batch, "height": H, "width": W,
               "parallelism": "replicas x%d (images shard across GPUs, no data-path collective)" % args.gpus,
               "l2": "4 rotating input batches (189 MB) + 2.9 GB activation working set >> 126 MB L2"}
@@ -251,6 +251,26 @@ def main():
                                    % which,
                     "share_of_step": head["ms"] / total, "conv_stack_tflops": all_tf,
                     "conv_stack_frac": all_tf / tf_sus}
+        # ------------------------------------------------------------ decode kernels (BASELINE metric: "decode HBM GB/s")
+        post = model.heads.post_processor
+        hp = model.heads.predictor.last_plan
+        meta = post.prepare_targets(targets, True, dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        dts = []
+        for rep in range(5):
+            flush.zero_()                                  # evict cls/reg from L2: the decode is their first reader
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            post.launch(hp.cls, hp.reg, meta)
+            d1.record()
+            torch.cuda.synchronize()
+            dts.append(d0.elapsed_time(d1))
+        dec_ms = sorted(dts)[len(dts) // 2]
+        dec_bytes = B * (3 * 96 * 320 * 4 + 50 * 50 * 4 + 50 * 14 * 4 + 1400)       # 382.8 KB / image
+        decode = {"bound": "hbm", "kernel": "nms_topk_stage1 + topk_decode_stage2", "achieved": dec_bytes / dec_ms / 1e6,
+                  "peak": hbm, "unit": "GB/s", "frac": dec_bytes / dec_ms / 1e6 / hbm, "ms": dec_ms,
+                  "algorithmic_bytes": dec_bytes,
+                  "note": "latency-bound by construction (SURVEY H7): %.1f us of pure DRAM time at peak" % (dec_bytes / hbm / 1e3)}
         if args.dump_launches:
             os.makedirs(os.path.dirname(os.path.abspath(args.dump_launches)), exist_ok=True)
             json.dump({"total_ms": total, "launches": table}, open(args.dump_launches, "w"), indent=1)
@@ -265,7 +285,8 @@ def main():
                 "config": config, "clocks": sampler.summary(),
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "decode_roofline": decode,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

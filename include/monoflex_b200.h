@@ -106,7 +106,8 @@ int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* str
 /* nms_hm + select_topk + select_point_of_interest + PostProcessor decode (model/layers/utils.py:45-145,
  * model/head/detector_infer.py:77-237, model/anno_encoder.py:69-295) for a whole batch.
  * heat [B,C,H,W] fp32 (apply_sigmoid=1: raw logits), reg [B,R=50,H,W] fp32, calib [B,6] = f_u,f_v,c_u,c_v,b_x,b_y,
- * pad [B,2], size [B,2] = (W,H) of the padded image, dim_mean [C,3]. Workspaces ws_score/ws_idx: [B*C*K].
+ * pad [B,2], size [B,2] = (W,H) of the padded image, dim_mean [C,3]. Workspaces ws_score/ws_idx: [B*C*K*8]
+ * (stage 1 runs 8 CTAs per (image, class) plane; stage 2 merges their candidates).
  * Outputs: scores/clses/ys/xs [B,K] fp32, inds [B,K] int64, pois [B,K,R], result [B,K,14], count [B] = #(score>=thresh). */
 int mf_decode_detections(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
                          const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,

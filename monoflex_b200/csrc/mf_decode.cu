@@ -14,8 +14,8 @@
 
 namespace mf {
 
+#define MF_DECODE_SLABS 8
 static constexpr int S1_THREADS = 1024;
-static constexpr int S1_ITEMS = 32;  // up to 32768 pixels per class map
 
 MF_DEVINL float heat_value(const float* __restrict__ hm, int H, int W, int y, int x, int apply_sigmoid) {
   float v = __ldg(hm + y * W + x);
@@ -28,11 +28,16 @@ MF_DEVINL float heat_value(const float* __restrict__ hm, int H, int W, int y, in
 
 // hm: [B, C, H, W] fp32 (already sigmoid-ed when apply_sigmoid == 0). out_*: [B, C, K]
 __global__ void __launch_bounds__(S1_THREADS)
-nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, int apply_sigmoid,
+nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, int apply_sigmoid, int slabs,
                        float* __restrict__ out_score, int* __restrict__ out_idx) {
+  // blockIdx.x = plane * slabs + slab; a slab is a contiguous pixel range [lo, hi) of one (image, class) plane. The union
+  // of the per-slab top-K sets contains the plane's top-K, so splitting only adds parallelism (148 SMs instead of B*C).
   const int HW = H * W;
-  const float* hm = hm_all + static_cast<long long>(blockIdx.x) * HW;
-  __shared__ unsigned int hist[256];
+  const int plane = blockIdx.x / slabs, slab = blockIdx.x - plane * slabs;
+  const int chunk = (HW + slabs - 1) / slabs;
+  const int lo = slab * chunk, hi = min(HW, lo + chunk);
+  const float* hm = hm_all + static_cast<long long>(plane) * HW;
+  __shared__ unsigned int hist[257];                  // bin 256 = "not a candidate" (keeps the warp converged)
   __shared__ unsigned long long sel[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_count;
@@ -41,15 +46,15 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
   // on the fly: key = ((bits << 15) | (32767 - idx)) + 1   (0 = "no pixel")
   extern __shared__ unsigned int vbits_sm[];      // [S1_ITEMS][S1_THREADS] score bits (dynamic smem, <= 128 KB)
   unsigned int* vbits = vbits_sm + threadIdx.x;   // item `it` of this thread lives at vbits[it * S1_THREADS]
-  const int n_items = (HW + S1_THREADS - 1) / S1_THREADS;
-#define MF_KEY(it) ((it) * S1_THREADS + static_cast<int>(threadIdx.x) < HW                                              \
+  const int n_items = (hi - lo + S1_THREADS - 1) / S1_THREADS;
+#define MF_KEY(it) (lo + (it) * S1_THREADS + static_cast<int>(threadIdx.x) < hi                                              \
                         ? ((static_cast<unsigned long long>(vbits[(it) * S1_THREADS]) << 15) |                                         \
-                           static_cast<unsigned long long>(32767 - ((it) * S1_THREADS + static_cast<int>(threadIdx.x)))) + 1ull \
+                           static_cast<unsigned long long>(32767 - (lo + (it) * S1_THREADS + static_cast<int>(threadIdx.x)))) + 1ull \
                         : 0ull)
   for (int it = 0; it < n_items; ++it) {
-    const int idx = it * S1_THREADS + threadIdx.x;
+    const int idx = lo + it * S1_THREADS + threadIdx.x;
     unsigned int key = 0u;
-    if (idx < HW) {
+    if (idx < hi) {
       const int y = idx / W, x = idx - y * W;
       const float v = heat_value(hm, H, W, y, x, apply_sigmoid);
       float mx = v;                                   // max_pool2d 3x3 s1 p1 (-inf padding): nms_hm utils.py:45-58
@@ -67,18 +72,23 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
     }
     vbits[it * S1_THREADS] = key;
   }
-  if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = K; }
+  const int k_eff = min(K, hi - lo);                  // a slab narrower than K keeps everything it has
+  if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = k_eff; }
   __syncthreads();
 
   // MSB-first radix select of the K-th largest key (48 significant bits -> 6 passes of 8 bits)
   for (int shift = 40; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += S1_THREADS) hist[i] = 0u;
+    for (int i = threadIdx.x; i < 257; i += S1_THREADS) hist[i] = 0u;
     __syncthreads();
     const unsigned long long prefix = s_prefix;
     const unsigned long long himask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
     for (int it = 0; it < n_items; ++it) {
       const unsigned long long k = MF_KEY(it);
-      if (k != 0ull && (k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255ull], 1u);
+      const unsigned int digit = (k != 0ull && (k & himask) == prefix) ? static_cast<unsigned int>((k >> shift) & 255ull) : 256u;
+      // warp-aggregated histogram: in the top passes every key of a warp has the same digit (same exponent bits), a plain
+      // atomicAdd would serialise 32-fold on one shared-memory address
+      const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+      if ((threadIdx.x & 31) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -138,9 +148,10 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
   }
 #undef MF_KEY
   if (threadIdx.x < K) {
-    const unsigned long long k = sel[threadIdx.x] - 1ull;
-    out_score[static_cast<long long>(blockIdx.x) * K + threadIdx.x] = __uint_as_float(static_cast<unsigned int>(k >> 15));
-    out_idx[static_cast<long long>(blockIdx.x) * K + threadIdx.x] = 32767 - static_cast<int>(k & 32767ull);
+    const bool have = threadIdx.x < k_eff;
+    const unsigned long long k = have ? sel[threadIdx.x] - 1ull : 0ull;
+    out_score[static_cast<long long>(blockIdx.x) * K + threadIdx.x] = have ? __uint_as_float(static_cast<unsigned int>(k >> 15)) : 0.f;
+    out_idx[static_cast<long long>(blockIdx.x) * K + threadIdx.x] = have ? 32767 - static_cast<int>(k & 32767ull) : -1;
   }
 }
 
@@ -175,7 +186,7 @@ struct DecodeParams {
   const float* pad;       // [B, 2]
   const float* size;      // [B, 2] (W, H) of the padded image (ParamsList.size)
   const float* dim_mean;  // [C, 3]
-  int B, C, K, R, H, W;
+  int B, C, K, R, H, W, S;
   float thresh;
   int down_ratio;
   // outputs
@@ -191,28 +202,39 @@ struct DecodeParams {
 
 // channel map runs/monoflex.yaml:27-28: 2d_dim 0:4 | 3d_offset 4:6 | corner_offset 6:26 | corner_uncertainty 26:29 |
 // 3d_dim 29:32 | ori_cls 32:40 | ori_offset 40:48 | depth 48 | depth_uncertainty 49
-__global__ void __launch_bounds__(256) topk_decode_stage2_kernel(const DecodeParams p) {
+static constexpr int S2_THREADS = 1024;
+static constexpr int S2_KEYS = 2048;
+
+__global__ void __launch_bounds__(S2_THREADS) topk_decode_stage2_kernel(const DecodeParams p) {
   const int b = blockIdx.x;
-  const int CK = p.C * p.K;                 // <= 256
-  __shared__ unsigned long long sel[256];
+  const int SK = p.S * p.K, CSK = p.C * SK;     // candidates per class / per image (<= 2048)
+  __shared__ unsigned long long sel[S2_KEYS];
   __shared__ float s_poi[64 * 50];
-  {
+  // key = score bits << 17 | (3 - class) << 15 | (32767 - pixel index): (score desc, class asc, index asc) is exactly the
+  // order of the reference's two-stage top-k (per class, then over the concatenated [class][rank] list, utils.py:61-100)
+  for (int i = threadIdx.x; i < S2_KEYS; i += S2_THREADS) {
     unsigned long long key = 0ull;
-    const int i = threadIdx.x;
-    if (i < CK) {
-      const float sc = p.s1_score[static_cast<long long>(b) * CK + i];
-      key = ((static_cast<unsigned long long>(__float_as_uint(sc)) << 8) | static_cast<unsigned long long>(255 - i)) + 1ull;
+    if (i < CSK) {
+      const int idx = p.s1_idx[static_cast<long long>(b) * CSK + i];
+      if (idx >= 0) {
+        const float sc = p.s1_score[static_cast<long long>(b) * CSK + i];
+        const int c = i / SK;
+        key = ((static_cast<unsigned long long>(__float_as_uint(sc)) << 17) | (static_cast<unsigned long long>(3 - c) << 15) |
+               static_cast<unsigned long long>(32767 - idx)) + 1ull;
+      }
     }
     sel[i] = key;
   }
   __syncthreads();
-  for (int size = 2; size <= 256; size <<= 1) {
+  for (int size = 2; size <= S2_KEYS; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const int i = threadIdx.x, jn = i ^ stride;
-      if (jn > i) {
-        const unsigned long long a = sel[i], c = sel[jn];
-        const bool desc = (i & size) == 0;
-        if (desc ? (a < c) : (a > c)) { sel[i] = c; sel[jn] = a; }
+      for (int i = threadIdx.x; i < S2_KEYS; i += S2_THREADS) {
+        const int jn = i ^ stride;
+        if (jn > i) {
+          const unsigned long long a = sel[i], c = sel[jn];
+          const bool desc = (i & size) == 0;
+          if (desc ? (a < c) : (a > c)) { sel[i] = c; sel[jn] = a; }
+        }
       }
       __syncthreads();
     }
@@ -222,8 +244,7 @@ __global__ void __launch_bounds__(256) topk_decode_stage2_kernel(const DecodePar
   for (int t = threadIdx.x; t < p.K * p.R; t += blockDim.x) {
     const int d = t / p.R, ch = t - d * p.R;
     const unsigned long long k = sel[d] - 1ull;
-    const int pos = 255 - static_cast<int>(k & 255ull);
-    const int idx = p.s1_idx[static_cast<long long>(b) * CK + pos];
+    const int idx = 32767 - static_cast<int>(k & 32767ull);
     const float v = __ldg(p.reg + (static_cast<long long>(b) * p.R + ch) * HW + idx);
     s_poi[d * p.R + ch] = v;
     p.pois[(static_cast<long long>(b) * p.K + d) * p.R + ch] = v;
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(256) topk_decode_stage2_kernel(const DecodePar
   if (threadIdx.x == 0) {
     int n = 0;
     for (int d = 0; d < p.K; ++d) {
-      const float sc = __uint_as_float(static_cast<unsigned int>((sel[d] - 1ull) >> 8));
+      const float sc = __uint_as_float(static_cast<unsigned int>((sel[d] - 1ull) >> 17));
       if (sc >= p.thresh) ++n;
     }
     p.count[b] = n;
@@ -240,10 +261,9 @@ __global__ void __launch_bounds__(256) topk_decode_stage2_kernel(const DecodePar
   const int d = threadIdx.x;
   if (d >= p.K) return;
   const unsigned long long k = sel[d] - 1ull;
-  const int pos = 255 - static_cast<int>(k & 255ull);
-  const float score = __uint_as_float(static_cast<unsigned int>(k >> 8));
-  const int cls = pos / p.K;
-  const int idx = p.s1_idx[static_cast<long long>(b) * CK + pos];
+  const float score = __uint_as_float(static_cast<unsigned int>(k >> 17));
+  const int cls = 3 - static_cast<int>((k >> 15) & 3ull);
+  const int idx = 32767 - static_cast<int>(k & 32767ull);
   const float yf = static_cast<float>(idx / p.W), xf = static_cast<float>(idx % p.W);
   const long long o = static_cast<long long>(b) * p.K + d;
   p.scores[o] = score; p.inds[o] = idx; p.clses[o] = static_cast<float>(cls); p.ys[o] = yf; p.xs[o] = xf;
@@ -322,11 +342,12 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
                   const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
                   float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
                   float* pois, float* result, int* count, cudaStream_t st) {
-  if (H * W > S1_THREADS * S1_ITEMS || C * K > 256 || K > 64 || R != 50) {
-    set_error("decode: unsupported shape H*W=%d C*K=%d K=%d R=%d", H * W, C * K, K, R);
+  const int S = MF_DECODE_SLABS;
+  if (H * W > 32768 || C > 3 || C * S * K > S2_KEYS || K > 64 || R != 50) {
+    set_error("decode: unsupported shape H*W=%d C=%d K=%d R=%d", H * W, C, K, R);
     return -1;
   }
-  const int n_items = (H * W + S1_THREADS - 1) / S1_THREADS;
+  const int n_items = ((H * W + S - 1) / S + S1_THREADS - 1) / S1_THREADS;
   const int s1_smem = n_items * S1_THREADS * static_cast<int>(sizeof(unsigned int));
   static int s1_attr = 0;
   if (s1_smem > s1_attr) {
@@ -335,14 +356,14 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
       return -1;
     s1_attr = s1_smem;
   }
-  nms_topk_stage1_kernel<<<B * C, S1_THREADS, s1_smem, st>>>(heat, H, W, K, apply_sigmoid, s1_score, s1_idx);
+  nms_topk_stage1_kernel<<<B * C * S, S1_THREADS, s1_smem, st>>>(heat, H, W, K, apply_sigmoid, S, s1_score, s1_idx);
   if (check_cuda(cudaGetLastError(), "nms_topk_stage1")) return -1;
   DecodeParams p;
   p.s1_score = s1_score; p.s1_idx = s1_idx; p.reg = reg; p.calib = calib; p.pad = pad; p.size = size;
-  p.dim_mean = dim_mean; p.B = B; p.C = C; p.K = K; p.R = R; p.H = H; p.W = W; p.thresh = thresh; p.down_ratio = 4;
+  p.dim_mean = dim_mean; p.B = B; p.C = C; p.K = K; p.R = R; p.H = H; p.W = W; p.S = S; p.thresh = thresh; p.down_ratio = 4;
   p.scores = scores; p.inds = inds; p.clses = clses; p.ys = ys; p.xs = xs; p.pois = pois; p.result = result;
   p.count = count;
-  topk_decode_stage2_kernel<<<B, 256, 0, st>>>(p);
+  topk_decode_stage2_kernel<<<B, S2_THREADS, 0, st>>>(p);
   return check_cuda(cudaGetLastError(), "topk_decode_stage2");
 }
 

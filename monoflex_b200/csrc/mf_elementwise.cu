@@ -175,9 +175,80 @@ __global__ void upsample_add_kernel(const __half* __restrict__ x, const float* _
   for (int e = 0; e < 8; ++e) acc[e] += up[e];
   *reinterpret_cast<uint4*>(y + pix * y_ld + cv * 8) = pack8(acc);
 }
+// f == 2 (k = 4, pad 1) specialisation: one thread produces the 2x2 output block {2a+1, 2a+2} x {2b+1, 2b+2}, which depends
+// on exactly the four inputs (a..a+1, b..b+1): each input vector is loaded once instead of four times and every one of
+// the 16 kernel taps is used exactly once.
+__global__ void upsample2_add_kernel(const __half* __restrict__ x, const float* __restrict__ w,
+                                     const __half* __restrict__ skip, __half* __restrict__ y, int B, int Hi, int Wi, int C,
+                                     int x_ld, int skip_ld, int y_ld) {
+  const int CV = C / 8, Ho = 2 * Hi, Wo = 2 * Wi;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * (Hi + 1) * (Wi + 1) * CV) return;
+  const int cv = static_cast<int>(i % CV);
+  long long t = i / CV;
+  const int bb = static_cast<int>(t % (Wi + 1)) - 1;
+  t /= (Wi + 1);
+  const int a = static_cast<int>(t % (Hi + 1)) - 1;
+  const long long b = t / (Hi + 1);
+  float in[2][2][8];
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+      const int yy = a + iy, xx = bb + ix;
+      if (yy >= 0 && yy < Hi && xx >= 0 && xx < Wi) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + yy) * Wi + xx) * x_ld + cv * 8)), in[iy][ix]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) in[iy][ix][e] = 0.f;
+      }
+    }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int oy = 2 * a + 1 + dy;
+    if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ox = 2 * bb + 1 + dx;
+      if (ox < 0 || ox >= Wo) continue;
+      const long long pix = (b * Ho + oy) * Wo + ox;
+      float acc[8], up[8];
+      if (skip != nullptr) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(skip + pix * skip_ld + cv * 8)), acc);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) up[e] = 0.f;
+      // same accumulation order as the generic kernel: input rows a+1 then a, columns b+1 then b
+#pragma unroll
+      for (int iy = 1; iy >= 0; --iy)
+#pragma unroll
+        for (int ix = 1; ix >= 0; --ix) {
+          const int ky = dy + 2 * (1 - iy), kx = dx + 2 * (1 - ix);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(ky * 4 + kx) * C + cv * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(ky * 4 + kx) * C + cv * 8 + 4));
+          const float* v = in[iy][ix];
+          up[0] += v[0] * w0.x; up[1] += v[1] * w0.y; up[2] += v[2] * w0.z; up[3] += v[3] * w0.w;
+          up[4] += v[4] * w1.x; up[5] += v[5] * w1.y; up[6] += v[6] * w1.z; up[7] += v[7] * w1.w;
+        }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += up[e];
+      *reinterpret_cast<uint4*>(y + pix * y_ld + cv * 8) = pack8(acc);
+    }
+  }
+}
+
 int launch_upsample_add(const __half* x, const float* w, const __half* skip, __half* y, int B, int Hi, int Wi, int C,
                         int f, int x_ld, int skip_ld, int y_ld, cudaStream_t st) {
   if (C % 8 || x_ld % 8 || y_ld % 8 || (skip && skip_ld % 8) || f < 1) { set_error("upsample_add: bad shape"); return -1; }
+  if (f == 2) {
+    const long long n2 = static_cast<long long>(B) * (Hi + 1) * (Wi + 1) * (C / 8);
+    upsample2_add_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(x, w, skip, y, B, Hi, Wi, C, x_ld, skip_ld,
+                                                                                 y_ld);
+    return check_cuda(cudaGetLastError(), "upsample2_add");
+  }
   const long long n = static_cast<long long>(B) * Hi * f * Wi * f * (C / 8);
   upsample_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, w, skip, y, B, Hi, Wi, C, f, x_ld,
                                                                                skip_ld, y_ld);

@@ -29,8 +29,9 @@ class DecodeWorkspace(object):
     def __init__(self, B, C, K, R, device):
         f = dict(dtype=torch.float32, device=device)
         self.B, self.C, self.K, self.R = B, C, K, R
-        self.ws_score = torch.empty(B * C * K, **f)
-        self.ws_idx = torch.empty(B * C * K, dtype=torch.int32, device=device)
+        slabs = 8     # MF_DECODE_SLABS: stage 1 splits every (image, class) plane into 8 pixel ranges
+        self.ws_score = torch.empty(B * C * K * slabs, **f)
+        self.ws_idx = torch.empty(B * C * K * slabs, dtype=torch.int32, device=device)
         self.scores, self.clses = torch.empty(B, K, **f), torch.empty(B, K, **f)
         self.ys, self.xs = torch.empty(B, K, **f), torch.empty(B, K, **f)
         self.inds = torch.empty(B, K, dtype=torch.long, device=device)
