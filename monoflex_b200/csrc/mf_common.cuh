@@ -49,6 +49,27 @@ MF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 MF_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ explicit shared-space ld/st
+// (pointers carved out of the dynamic smem block through integer alignment lose their address space: the compiler then
+// emits generic LD.E / ST.E with 64-bit address arithmetic; these keep the hot loops on LDS / STS with 32-bit addresses)
+MF_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+MF_DEVINL float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+MF_DEVINL void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+MF_DEVINL void sts128f(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+MF_DEVINL void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------ cp.async
 // 16-byte global->shared copy; src_bytes == 0 zero-fills the destination (used for conv padding / K tail).
 MF_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {

@@ -161,6 +161,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     constexpr int NCHUNK = BLOCK_N / CHUNK;
     constexpr int NGROUPS = EPI_THREADS / 128;
     const bool staged = use_tma_store != 0;             // host guarantees OUT_F16_NHWC && BLOCK_N >= 64
+    const uint32_t sc_u = smem_u32(sc_s), sh_u = smem_u32(sh_s), o_u = smem_u32(o_smem);
     int ti = -1;
     MF_TILE_LOOP {
       ++ti;
@@ -182,8 +183,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
       if (staged && et == 0) bulk_wait_read0();         // previous tile's TMA store has finished reading the staging
       if (et < BLOCK_N) {
-        sc_s[et] = __ldg(p.scale + n0 + et);
-        sh_s[et] = __ldg(p.shift + n0 + et);
+        sts32f(sc_u + et * 4, __ldg(p.scale + n0 + et));
+        sts32f(sh_u + et * 4, __ldg(p.shift + n0 + et));
       }
       bar_sync_named(1, EPI_THREADS);
       mbar_wait(&acc_full[acc], (ti >> 1) & 1);
@@ -208,8 +209,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         float v[CHUNK];
 #pragma unroll
         for (int i = 0; i < CHUNK; i += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sc_s + ch * CHUNK + i);
-          const float4 h4 = *reinterpret_cast<const float4*>(sh_s + ch * CHUNK + i);
+          const float4 s4 = lds128f(sc_u + (ch * CHUNK + i) * 4);
+          const float4 h4 = lds128f(sh_u + (ch * CHUNK + i) * 4);
           v[i] = __uint_as_float(r[i]) * s4.x + h4.x;
           v[i + 1] = __uint_as_float(r[i + 1]) * s4.y + h4.y;
           v[i + 2] = __uint_as_float(r[i + 2]) * s4.z + h4.z;
@@ -235,13 +236,13 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         if (p.out_mode == OUT_F16_NHWC) {
           if (staged) {
             if constexpr (BLOCK_N >= 64) {
-              uint8_t* sub = o_smem + (ch >> 1) * A_STAGE;
+              const uint32_t sub = o_u + (ch >> 1) * A_STAGE;
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 8) {
                 __half2 o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(sub + sw128_off(row, (ch & 1) * 4 + (i >> 3))) = *reinterpret_cast<uint4*>(o);
+                sts128(sub + sw128_off(row, (ch & 1) * 4 + (i >> 3)), *reinterpret_cast<uint4*>(o));
               }
             }
           } else if (mvalid) {
@@ -358,8 +359,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       // the modulation mask (0 for corners / samples outside the image, dcn_v2_im2col_cuda.cu:37-48,180) and the 4
       // corner pixel indices (clamped, so the gather needs no predication). The reference recomputes this per channel;
       // the first version of this kernel per 8-channel chunk. Phase G then is pure load / blend / store.
-      float4* prm_w = reinterpret_cast<float4*>(prm_smem);
-      int4* prm_o = reinterpret_cast<int4*>(prm_smem + 9 * BM * 16);
+      const uint32_t prm_w = smem_u32(prm_smem);                    // [9*128] float4 weights
+      const uint32_t prm_o = prm_w + 9 * BM * 16;                    // [9*128] int4 corner pixel indices
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -392,22 +393,23 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               o = make_int4(hlc * p.W + wlc, hlc * p.W + wic, hic * p.W + wlc, hic * p.W + wic);
             }
           }
-          prm_w[item] = w;
-          prm_o[item] = o;
+          sts128f(prm_w + item * 16, w);
+          sts128(prm_o + item * 16, make_uint4(o.x, o.y, o.z, o.w));
         }
         bar_sync_named(2, NPT);
         const __half* x_img = p.x + static_cast<long long>(tile_b) * p.H * p.W * p.x_ld + j * 8;
         int tap = 0, c0 = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_stage = a_smem + stage * A_STAGE;
+          const uint32_t a_stage = smem_u32(a_smem + stage * A_STAGE);
           uint4 v[PASSES][4];
           float4 wq[PASSES];
 #pragma unroll
           for (int q = 0; q < PASSES; ++q) {               // all loads of the K block first (memory-level parallelism)
             const int r = q * RPP + rsub;
-            wq[q] = prm_w[tap * BM + r];
-            const int4 o = prm_o[tap * BM + r];
+            wq[q] = lds128f(prm_w + (tap * BM + r) * 16);
+            const uint4 ou = lds128(prm_o + (tap * BM + r) * 16);
+            const int4 o = make_int4(ou.x, ou.y, ou.z, ou.w);
             const __half* xb = x_img + c0;
             v[q][0] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.x) * p.x_ld));
             v[q][1] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.y) * p.x_ld));
@@ -430,7 +432,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               const float vy = wq[q].x * f1.y + wq[q].y * f2.y + wq[q].z * f3.y + wq[q].w * f4.y;
               o2[e] = __floats2half2_rn(vx, vy);
             }
-            *reinterpret_cast<uint4*>(a_stage + sw128_off(r, j)) = *reinterpret_cast<uint4*>(o2);
+            sts128(a_stage + sw128_off(r, j), *reinterpret_cast<uint4*>(o2));
           }
           fence_proxy_async();
           mbar_arrive(&full_bar[stage]);
