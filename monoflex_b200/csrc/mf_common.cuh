@@ -70,6 +70,28 @@ MF_DEVINL void sts128f(uint32_t addr, const float4& v) {
 }
 MF_DEVINL void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
+// ------------------------------------------------------------------------------------------------ packed fp32 math (sm_100: FFMA2 / FMUL2)
+MF_DEVINL unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+MF_DEVINL float2 f2_unpack(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+MF_DEVINL unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+MF_DEVINL unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------ cp.async
 // 16-byte global->shared copy; src_bytes == 0 zero-fills the destination (used for conv padding / K tail).
 MF_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {

@@ -390,49 +390,56 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               w.z = (bt && lf) ? lh * hw * mk : 0.f;
               w.w = (bt && rt) ? lh * lw * mk : 0.f;
               const int hlc = max(hl, 0), hic = min(hi, p.H - 1), wlc = max(wl, 0), wic = min(wi, p.W - 1);
-              o = make_int4(hlc * p.W + wlc, hlc * p.W + wic, hic * p.W + wlc, hic * p.W + wic);
+              const int pb = p.x_ld * 2;                      // bytes per pixel: records hold 32-bit BYTE offsets
+              o = make_int4((hlc * p.W + wlc) * pb, (hlc * p.W + wic) * pb, (hic * p.W + wlc) * pb, (hic * p.W + wic) * pb);
             }
           }
           sts128f(prm_w + item * 16, w);
           sts128(prm_o + item * 16, make_uint4(o.x, o.y, o.z, o.w));
         }
         bar_sync_named(2, NPT);
-        const __half* x_img = p.x + static_cast<long long>(tile_b) * p.H * p.W * p.x_ld + j * 8;
+        const char* x_img = reinterpret_cast<const char*>(p.x + static_cast<long long>(tile_b) * p.H * p.W * p.x_ld + j * 8);
         int tap = 0, c0 = 0;
+        uint32_t dst_off[PASSES];
+#pragma unroll
+        for (int q = 0; q < PASSES; ++q) dst_off[q] = sw128_off(q * RPP + rsub, j);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t a_stage = smem_u32(a_smem + stage * A_STAGE);
           uint4 v[PASSES][4];
           float4 wq[PASSES];
+          const char* xb = x_img + c0 * 2;
+          const uint32_t rec = (tap * BM + rsub) * 16;
 #pragma unroll
           for (int q = 0; q < PASSES; ++q) {               // all loads of the K block first (memory-level parallelism)
-            const int r = q * RPP + rsub;
-            wq[q] = lds128f(prm_w + (tap * BM + r) * 16);
-            const uint4 ou = lds128(prm_o + (tap * BM + r) * 16);
-            const int4 o = make_int4(ou.x, ou.y, ou.z, ou.w);
-            const __half* xb = x_img + c0;
-            v[q][0] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.x) * p.x_ld));
-            v[q][1] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.y) * p.x_ld));
-            v[q][2] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.z) * p.x_ld));
-            v[q][3] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(o.w) * p.x_ld));
+            wq[q] = lds128f(prm_w + rec + q * RPP * 16);
+            const uint4 o = lds128(prm_o + rec + q * RPP * 16);
+            v[q][0] = __ldg(reinterpret_cast<const uint4*>(xb + o.x));
+            v[q][1] = __ldg(reinterpret_cast<const uint4*>(xb + o.y));
+            v[q][2] = __ldg(reinterpret_cast<const uint4*>(xb + o.z));
+            v[q][3] = __ldg(reinterpret_cast<const uint4*>(xb + o.w));
           }
 #pragma unroll
           for (int q = 0; q < PASSES; ++q) {
-            const int r = q * RPP + rsub;
             const __half2* h1 = reinterpret_cast<const __half2*>(&v[q][0]);
             const __half2* h2 = reinterpret_cast<const __half2*>(&v[q][1]);
             const __half2* h3 = reinterpret_cast<const __half2*>(&v[q][2]);
             const __half2* h4 = reinterpret_cast<const __half2*>(&v[q][3]);
+            const unsigned long long w1 = f2_pack(wq[q].x, wq[q].x), w2 = f2_pack(wq[q].y, wq[q].y);
+            const unsigned long long w3 = f2_pack(wq[q].z, wq[q].z), w4 = f2_pack(wq[q].w, wq[q].w);
             __half2 o2[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; ++e) {                  // two channels per FFMA2 (packed fp32 math of sm_100)
               const float2 f1 = __half22float2(h1[e]), f2 = __half22float2(h2[e]);
               const float2 f3 = __half22float2(h3[e]), f4 = __half22float2(h4[e]);
-              const float vx = wq[q].x * f1.x + wq[q].y * f2.x + wq[q].z * f3.x + wq[q].w * f4.x;
-              const float vy = wq[q].x * f1.y + wq[q].y * f2.y + wq[q].z * f3.y + wq[q].w * f4.y;
-              o2[e] = __floats2half2_rn(vx, vy);
+              unsigned long long acc = f2_mul(w1, f2_pack(f1.x, f1.y));
+              acc = f2_fma(w2, f2_pack(f2.x, f2.y), acc);
+              acc = f2_fma(w3, f2_pack(f3.x, f3.y), acc);
+              acc = f2_fma(w4, f2_pack(f4.x, f4.y), acc);
+              const float2 r2 = f2_unpack(acc);
+              o2[e] = __floats2half2_rn(r2.x, r2.y);
             }
-            sts128(a_stage + sw128_off(r, j), *reinterpret_cast<uint4*>(o2));
+            sts128(a_stage + dst_off[q], *reinterpret_cast<uint4*>(o2));
           }
           fence_proxy_async();
           mbar_arrive(&full_bar[stage]);

@@ -34,21 +34,21 @@ def pick(plan, name, pred):
     raise KeyError(name)
 
 
-sel = [
-    ("head", pick(hp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 2304)),
-    ("dcn64", pick(bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 64 and a[3] == 96)),
-    ("offconv64", pick(bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 27 and a[5] == 64 and a[3] == 96)),
-    ("conv128", pick(bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 128 and a[5] == 128 and a[9] == 3)),
-    ("conv64", pick(bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 64 and a[5] == 64 and a[9] == 3)),
-    ("stem", pick(bp, "mf_conv2d_nhwc_f16", lambda a: a[9] == 7)),
-    ("level0", pick(bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 16 and a[5] == 16)),
-    ("upadd", pick(bp, "mf_upsample_add_nhwc_f16", lambda a: a[6] == 160)),
+sel_spec = [
+    ("head", hp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 2304),
+    ("dcn64", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 64 and a[3] == 96),
+    ("dcn128", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 128 and a[3] == 48),
+    ("offconv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 27 and a[5] == 64 and a[3] == 96),
+    ("conv128", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 128 and a[5] == 128 and a[9] == 3),
+    ("conv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 64 and a[5] == 64 and a[9] == 3),
+    ("stem", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 8),
+    ("level0", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 16 and a[5] == 1),
+    ("upadd", bp, "mf_upsample_add_nhwc_f16", lambda a: a[6] == 160),
 ]
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 only = os.environ.get("ONLY")
+sel = [(n, pick(pl, k, pred)) for n, pl, k, pred in sel_spec if not only or n in only.split(",")]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for name, (fn, args, n) in sel:
-    if only and name not in only.split(","):
-        continue
     flush.zero_()                      # L2 flush before each profiled launch (outside the profiler range)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
