@@ -30,6 +30,7 @@ MF_DEVINL float heat_value(const float* __restrict__ hm, int H, int W, int y, in
 __global__ void __launch_bounds__(S1_THREADS)
 nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, int apply_sigmoid, int slabs,
                        float* __restrict__ out_score, int* __restrict__ out_idx) {
+  pdl_wait();
   // blockIdx.x = plane * slabs + slab; a slab is a contiguous pixel range [lo, hi) of one (image, class) plane. The union
   // of the per-slab top-K sets contains the plane's top-K, so splitting only adds parallelism (148 SMs instead of B*C).
   const int HW = H * W;
@@ -157,6 +158,7 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
 
 // stand-alone nms_hm (model/layers/utils.py:45-58): out = heat * (maxpool3x3(heat) == heat)
 __global__ void nms_hm_kernel(const float* __restrict__ hm, float* __restrict__ out, int H, int W, long long n) {
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int HW = H * W;
@@ -174,7 +176,7 @@ __global__ void nms_hm_kernel(const float* __restrict__ hm, float* __restrict__ 
 }
 int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st) {
   const long long n = static_cast<long long>(planes) * H * W;
-  nms_hm_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(hm, out, H, W, n);
+  (void)launch_k(nms_hm_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, hm, out, H, W, n);
   return check_cuda(cudaGetLastError(), "nms_hm");
 }
 
@@ -206,6 +208,7 @@ static constexpr int S2_THREADS = 1024;
 static constexpr int S2_KEYS = 2048;
 
 __global__ void __launch_bounds__(S2_THREADS) topk_decode_stage2_kernel(const DecodeParams p) {
+  pdl_wait();
   const int b = blockIdx.x;
   const int SK = p.S * p.K, CSK = p.C * SK;     // candidates per class / per image (<= 2048)
   __shared__ unsigned long long sel[S2_KEYS];
@@ -356,14 +359,14 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
       return -1;
     s1_attr = s1_smem;
   }
-  nms_topk_stage1_kernel<<<B * C * S, S1_THREADS, s1_smem, st>>>(heat, H, W, K, apply_sigmoid, S, s1_score, s1_idx);
+  (void)launch_k(nms_topk_stage1_kernel, dim3(B * C * S), dim3(S1_THREADS), s1_smem, st, heat, H, W, K, apply_sigmoid, S, s1_score, s1_idx);
   if (check_cuda(cudaGetLastError(), "nms_topk_stage1")) return -1;
   DecodeParams p;
   p.s1_score = s1_score; p.s1_idx = s1_idx; p.reg = reg; p.calib = calib; p.pad = pad; p.size = size;
   p.dim_mean = dim_mean; p.B = B; p.C = C; p.K = K; p.R = R; p.H = H; p.W = W; p.S = S; p.thresh = thresh; p.down_ratio = 4;
   p.scores = scores; p.inds = inds; p.clses = clses; p.ys = ys; p.xs = xs; p.pois = pois; p.result = result;
   p.count = count;
-  topk_decode_stage2_kernel<<<B, S2_THREADS, 0, st>>>(p);
+  (void)launch_k(topk_decode_stage2_kernel, dim3(B), dim3(S2_THREADS), 0, st, p);
   return check_cuda(cudaGetLastError(), "topk_decode_stage2");
 }
 

@@ -23,6 +23,7 @@ MF_DEVINL uint4 pack8(const float (&f)[8]) {
 
 // ---------------------------------------------------------------- image: NCHW fp32 [B,3,H,W] -> NHWC fp16 [B,H,W,8]
 __global__ void pack_image_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int C, long long HW) {
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= B * HW) return;
   const long long b = i / HW, pix = i - b * HW;
@@ -34,12 +35,13 @@ __global__ void pack_image_kernel(const float* __restrict__ x, __half* __restric
 int launch_pack_image(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st) {
   if (C > 8) { set_error("pack_image: C=%d > 8", C); return -1; }
   const long long n = static_cast<long long>(B) * H * W;
-  pack_image_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, y, B, C, static_cast<long long>(H) * W);
+  (void)launch_k(pack_image_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, y, B, C, static_cast<long long>(H) * W);
   return check_cuda(cudaGetLastError(), "pack_image");
 }
 
 // ---------------------------------------------------------------- generic NCHW fp32 <-> NHWC fp16 (tile transpose)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, int HW, int y_ld) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -54,10 +56,11 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restr
 }
 int launch_nchw_to_nhwc(const float* x, __half* y, int B, int C, int HW, int y_ld, cudaStream_t st) {
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(x, y, C, HW, y_ld);
+  (void)launch_k(nchw_to_nhwc_kernel, dim3(grid), dim3(block), 0, st, x, y, C, HW, y_ld);
   return check_cuda(cudaGetLastError(), "nchw_to_nhwc");
 }
 __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int C, int HW, int x_ld) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -72,13 +75,14 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, float* __restr
 }
 int launch_nhwc_to_nchw(const __half* x, float* y, int B, int C, int HW, int x_ld, cudaStream_t st) {
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, st>>>(x, y, C, HW, x_ld);
+  (void)launch_k(nhwc_to_nchw_kernel, dim3(grid), dim3(block), 0, st, x, y, C, HW, x_ld);
   return check_cuda(cudaGetLastError(), "nhwc_to_nchw");
 }
 
 // offset [B,18,H,W] + mask [B,9,H,W] (fp32 NCHW, reference _ext layout) -> [B*H*W, 32] fp32 rows
 __global__ void pack_offmask_kernel(const float* __restrict__ off, const float* __restrict__ mask, float* __restrict__ y,
                                     int B, int HW) {
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * HW * 32) return;
   const int ch = static_cast<int>(i & 31);
@@ -91,13 +95,14 @@ __global__ void pack_offmask_kernel(const float* __restrict__ off, const float* 
 }
 int launch_pack_offmask(const float* off, const float* mask, float* y, int B, int HW, cudaStream_t st) {
   const long long n = static_cast<long long>(B) * HW * 32;
-  pack_offmask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(off, mask, y, B, HW);
+  (void)launch_k(pack_offmask_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, off, mask, y, B, HW);
   return check_cuda(cudaGetLastError(), "pack_offmask");
 }
 
 // ---------------------------------------------------------------- MaxPool2d(2) NHWC fp16 (dla_dcn.py:238)
 __global__ void maxpool2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int H, int W, int C,
                                 int x_ld, int y_ld) {
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, CV = C / 8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * Ho * Wo * CV) return;
@@ -125,7 +130,7 @@ __global__ void maxpool2_kernel(const __half* __restrict__ x, __half* __restrict
 int launch_maxpool2(const __half* x, __half* y, int B, int H, int W, int C, int x_ld, int y_ld, cudaStream_t st) {
   if (C % 8 || x_ld % 8 || y_ld % 8 || H % 2 || W % 2) { set_error("maxpool2: bad shape"); return -1; }
   const long long n = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, y, B, H, W, C, x_ld, y_ld);
+  (void)launch_k(maxpool2_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, y, B, H, W, C, x_ld, y_ld);
   return check_cuda(cudaGetLastError(), "maxpool2");
 }
 
@@ -135,6 +140,7 @@ int launch_maxpool2(const __half* x, __half* y, int B, int H, int W, int C, int 
 __global__ void upsample_add_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                                     const __half* __restrict__ skip, __half* __restrict__ y, int B, int Hi, int Wi,
                                     int C, int f, int x_ld, int skip_ld, int y_ld) {
+  pdl_wait();
   const int Ho = Hi * f, Wo = Wi * f, CV = C / 8, k = 2 * f, pad = f / 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * Ho * Wo * CV) return;
@@ -181,6 +187,7 @@ __global__ void upsample_add_kernel(const __half* __restrict__ x, const float* _
 __global__ void upsample2_add_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                                      const __half* __restrict__ skip, __half* __restrict__ y, int B, int Hi, int Wi, int C,
                                      int x_ld, int skip_ld, int y_ld) {
+  pdl_wait();
   const int CV = C / 8, Ho = 2 * Hi, Wo = 2 * Wi;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * (Hi + 1) * (Wi + 1) * CV) return;
@@ -245,12 +252,12 @@ int launch_upsample_add(const __half* x, const float* w, const __half* skip, __h
   if (C % 8 || x_ld % 8 || y_ld % 8 || (skip && skip_ld % 8) || f < 1) { set_error("upsample_add: bad shape"); return -1; }
   if (f == 2) {
     const long long n2 = static_cast<long long>(B) * (Hi + 1) * (Wi + 1) * (C / 8);
-    upsample2_add_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(x, w, skip, y, B, Hi, Wi, C, x_ld, skip_ld,
+    (void)launch_k(upsample2_add_kernel, dim3(static_cast<unsigned>((n2 + 255) / 256)), dim3(256), 0, st, x, w, skip, y, B, Hi, Wi, C, x_ld, skip_ld,
                                                                                  y_ld);
     return check_cuda(cudaGetLastError(), "upsample2_add");
   }
   const long long n = static_cast<long long>(B) * Hi * f * Wi * f * (C / 8);
-  upsample_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, w, skip, y, B, Hi, Wi, C, f, x_ld,
+  (void)launch_k(upsample_add_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, w, skip, y, B, Hi, Wi, C, f, x_ld,
                                                                                skip_ld, y_ld);
   return check_cuda(cudaGetLastError(), "upsample_add");
 }
@@ -261,6 +268,7 @@ int launch_upsample_add(const __half* x, const float* w, const __half* skip, __h
 __global__ void edge_gather_kernel(const __half* __restrict__ feat, int feat_ld, int ch_a, int ch_b,
                                    const long long* __restrict__ edge_idx, __half* __restrict__ ea,
                                    __half* __restrict__ eb, int B, int H, int W, int K, int out_w, int out_h) {
+  pdl_wait();
   const int CV = 32;  // 256 channels / 8
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * (K + 2) * CV * 2) return;
@@ -304,7 +312,7 @@ __global__ void edge_gather_kernel(const __half* __restrict__ feat, int feat_ld,
 int launch_edge_gather(const __half* feat, int feat_ld, int ch_a, int ch_b, const long long* edge_idx, __half* ea,
                        __half* eb, int B, int H, int W, int K, int out_w, int out_h, cudaStream_t st) {
   const long long n = static_cast<long long>(B) * (K + 2) * 32 * 2;
-  edge_gather_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(feat, feat_ld, ch_a, ch_b, edge_idx, ea, eb,
+  (void)launch_k(edge_gather_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, feat, feat_ld, ch_a, ch_b, edge_idx, ea, eb,
                                                                               B, H, W, K, out_w, out_h);
   return check_cuda(cudaGetLastError(), "edge_gather");
 }
@@ -315,6 +323,7 @@ __global__ void edge_head_add_kernel(const __half* __restrict__ t, const float* 
                                      const float* __restrict__ bias, int n_out, const long long* __restrict__ edge_idx,
                                      const long long* __restrict__ edge_len, float* __restrict__ out, int out_ctot,
                                      int out_ch0, int B, int K, int H, int W) {
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * K) return;
   const int b = warp / K, e = warp - b * K;
@@ -335,20 +344,21 @@ int launch_edge_head_add(const __half* t, const float* w, const float* bias, int
                          const long long* edge_len, float* out, int out_ctot, int out_ch0, int B, int K, int H, int W,
                          cudaStream_t st) {
   const long long threads = static_cast<long long>(B) * K * 32;
-  edge_head_add_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(t, w, bias, n_out, edge_idx, edge_len,
+  (void)launch_k(edge_head_add_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, t, w, bias, n_out, edge_idx, edge_len,
                                                                                      out, out_ctot, out_ch0, B, K, H, W);
   return check_cuda(cudaGetLastError(), "edge_head_add");
 }
 
 // sigmoid_hm (model/layers/utils.py:39-43): x = clamp(sigmoid(x), 1e-4, 1-1e-4), in place
 __global__ void sigmoid_clamp_kernel(float* __restrict__ x, long long n) {
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float s = 1.f / (1.f + expf(-x[i]));
   x[i] = fminf(fmaxf(s, 1e-4f), 1.f - 1e-4f);
 }
 int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st) {
-  sigmoid_clamp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, n);
+  (void)launch_k(sigmoid_clamp_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, n);
   return check_cuda(cudaGetLastError(), "sigmoid_clamp");
 }
 
@@ -356,6 +366,7 @@ int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st) {
 // out[0] += -(sum_pos log(p)(1-p)^2 + sum_neg log(1-p) p^2 (1-t)^4), out[1] += #(t==1).  (alpha=2, beta=4)
 __global__ void focal_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n,
                                   float* __restrict__ out) {
+  pdl_wait();
   float loss = 0.f, npos = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -392,7 +403,7 @@ int launch_focal_loss(const float* pred, const float* tgt, long long n, float* o
   if (check_cuda(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st), "focal memset")) return -1;
   long long blocks = (n + 1023) / 1024;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  focal_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(pred, tgt, n, out2);
+  (void)launch_k(focal_loss_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pred, tgt, n, out2);
   return check_cuda(cudaGetLastError(), "focal_loss");
 }
 

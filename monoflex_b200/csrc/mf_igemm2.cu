@@ -100,6 +100,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   constexpr int RPP = NPT / 8;
   constexpr int PASSES = BM / RPP;
 
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -152,6 +153,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();            // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   // ================================================================ epilogue body (run by 1 or 2 warp groups)
   auto run_epilogue = [&](const int group, const int et) {
@@ -621,8 +623,7 @@ static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUten
   const int ntm = MODE == MODE_DCN ? p.B * ((p.H + 7) / 8) * ((p.W + 15) / 16) : (p.M + BM - 1) / BM;
   int grid = num_sms() * C::CTAS_PER_SM;
   if (grid > ntn * ntm) grid = ntn * ntm;
-  kern<<<grid, (NPW + 6) * 32, smem, st>>>(tw, ty, tx, p, use_tma_store);
-  return check_cuda(cudaGetLastError(), "igemm2 launch");
+  return check_cuda(launch_k(kern, dim3(grid), dim3((NPW + 6) * 32), smem, st, tw, ty, tx, p, use_tma_store), "igemm2 launch");
 }
 
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {

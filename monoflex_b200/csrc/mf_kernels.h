@@ -35,7 +35,6 @@ struct IgemmParams {
   int y_ld;
 };
 
-extern int g_tunable[16];
 int igemm_block_n(int cout);
 int launch_igemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);

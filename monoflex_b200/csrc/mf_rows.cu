@@ -54,6 +54,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 2)
 rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ RowsParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = p.nseg * SEG_BYTES;                 // multiple of 128
@@ -86,6 +87,7 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ================================================================ TMA: resident weights, then row segments per tile
@@ -313,14 +315,14 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
       if (check_cuda(cudaFuncSetAttribute(rows_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "rows smem")) return -1;
       attr = smem;
     }
-    rows_conv_kernel<16><<<grid, 192, smem, st>>>(tx, tw, p);
+    if (check_cuda(launch_k(rows_conv_kernel<16>, dim3(grid), dim3(192), smem, st, tx, tw, p), "rows_conv launch")) return -1;
   } else {
     static int attr = 0;
     if (smem > attr) {
       if (check_cuda(cudaFuncSetAttribute(rows_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "rows smem")) return -1;
       attr = smem;
     }
-    rows_conv_kernel<32><<<grid, 192, smem, st>>>(tx, tw, p);
+    if (check_cuda(launch_k(rows_conv_kernel<32>, dim3(grid), dim3(192), smem, st, tx, tw, p), "rows_conv launch")) return -1;
   }
   return check_cuda(cudaGetLastError(), "rows_conv launch");
 }
