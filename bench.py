@@ -169,8 +169,9 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        out = step(dev_imgs[i % n_in])
+    with torch.no_grad():
+        for i in range(args.steps):
+            pending = model.forward_async(dev_imgs[i % n_in], targets)     # no host sync inside the device-resident loop
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -196,17 +197,20 @@ def main():
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     prefetch(0)
-    d2h = 0
-    for i in range(args.steps):
-        j = i % 2
-        if i + 1 < args.steps:
-            prefetch(i + 1)
-        torch.cuda.current_stream().wait_event(ready[j])
-        res, eu, _ = step(bufs[j])
-        done[j].record()
-        n = res.shape[0]
-        host_out[:n].copy_(res, non_blocking=True)
-        d2h = n * 14 * 4 + 4 * B
+    d2h, prev = 0, None
+    with torch.no_grad():
+        for i in range(args.steps):
+            j = i % 2
+            if i + 1 < args.steps:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[j])
+            cur = model.forward_async(bufs[j], targets).stage()           # H2D done -> forward -> async D2H of the detections
+            done[j].record()
+            if prev is not None:                                           # read step i-1 on the host while step i runs
+                res, counts = prev.result()
+            prev = cur
+        res, counts = prev.result()
+        d2h = B * 50 * 14 * 4 + 4 * B
     t1.record()
     torch.cuda.synchronize()
     ms_e2e = t0.elapsed_time(t1)

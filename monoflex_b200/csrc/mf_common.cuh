@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 extern int g_tunable[16];
 
-// <<<>>> replacement that adds the programmatic-stream-serialization attribute (tunable 8 == 1 turns it off)
+// <<<>>> replacement that can add the programmatic-stream-serialization attribute (tunable 8 == 1 turns it on)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -27,15 +27,15 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_tunable[8] == 1 ? 0 : 1;
+  cfg.numAttrs = g_tunable[8] == 1 ? 1 : 0;       // measured: no gain under CUDA-graph replay (A/B 1588 vs 1595 img/s) -> opt-in
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 MF_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // ------------------------------------------------------------------------------------------------ programmatic dependent launch
-// Every kernel of the plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start while its
-// predecessor is still draining. `pdl_launch_dependents()` (first statement) lets the successor's CTAs be scheduled as
+// With tunable 8 every kernel of the plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start
+// while its predecessor is still draining (without the attribute the two instructions below are no-ops). `pdl_launch_dependents()` (first statement) lets the successor's CTAs be scheduled as
 // soon as SM resources free up; `pdl_wait()` blocks until the predecessor grid has completed and its writes are visible,
 // and must precede the first access to any buffer another kernel produces or still reads.
 MF_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -38,8 +38,25 @@ class KeypointDetector(nn.Module):
             return self.heads(features, targets, test=self.test)
         return self._forward_graph(x, targets)
 
+    def forward_async(self, images, targets):
+        """Enqueue one eval forward (graph replay) and return a handle; `handle.result()` waits for it and returns what
+        `forward` returns. Lets a caller overlap the host-side read of step i with the GPU work of step i+1 (the decode
+        workspace is re-used by the next forward, so call `result()` - or at least `stage()` - before the forward after
+        next)."""
+        if self.training:
+            raise RuntimeError("forward_async is an inference API")
+        x = to_image_list(images).tensors
+        if not x.is_cuda:
+            raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
+        g = self._enqueue_graph(x, targets)
+        return PendingDetections(self.heads.post_processor, g['ws'], g['plan_h'].cls)
+
     # ------------------------------------------------------------------ CUDA-graph path
     def _forward_graph(self, x, targets):
+        g = self._enqueue_graph(x, targets)
+        return self.heads.post_processor.finish(g['ws'], g['plan_h'].cls)
+
+    def _enqueue_graph(self, x, targets):
         pred, post = self.heads.predictor, self.heads.post_processor
         post.check_config()
         x = x.float().contiguous()
@@ -55,7 +72,7 @@ class KeypointDetector(nn.Module):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         g['graph'].replay()
-        return post.finish(g['ws'], g['plan_h'].cls)
+        return g
 
     def _capture(self, x, targets, key):
         pred, post = self.heads.predictor, self.heads.post_processor
@@ -76,3 +93,36 @@ class KeypointDetector(nn.Module):
             ws = body()
         self._graph = {'key': key, 'graph': graph, 'x': xs, 'plan_b': plan_b, 'plan_h': plan_h, 'meta': meta, 'ws': ws}
         return self._graph
+
+
+class PendingDetections(object):
+    """Handle of an enqueued forward: `stage()` starts the device->host copy of the padded detections + counts into
+    pinned buffers (asynchronous, stream ordered), `result()` waits for it and slices on the host."""
+
+    def __init__(self, post, ws, heat):
+        self.post, self.ws, self.heat = post, ws, heat
+        self._staged = None
+
+    def stage(self):
+        if self._staged is None:
+            ws = self.ws
+            host = getattr(ws, "_pinned", None)
+            if host is None:
+                host = ws._pinned = [(torch.empty(ws.result.shape).pin_memory(), torch.empty(ws.count.shape, dtype=torch.int32).pin_memory(),
+                                      torch.cuda.Event()) for _ in range(2)]
+                ws._pin_i = 0
+            res_h, cnt_h, ev = host[ws._pin_i]
+            ws._pin_i ^= 1
+            res_h.copy_(ws.result, non_blocking=True)
+            cnt_h.copy_(ws.count, non_blocking=True)
+            ev.record()
+            self._staged = (res_h, cnt_h, ev)
+        return self
+
+    def result(self):
+        """-> (result[N,14] on the HOST, counts list): the rows `forward` would return, read through pinned memory."""
+        res_h, cnt_h, ev = self.stage()._staged
+        ev.synchronize()
+        counts = cnt_h.tolist()
+        rows = [res_h[b, :n] for b, n in enumerate(counts)]
+        return (torch.cat(rows, 0) if len(rows) > 1 else rows[0].clone()), counts

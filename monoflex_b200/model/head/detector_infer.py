@@ -42,20 +42,21 @@ class PostProcessor(nn.Module):
         self._meta_cache = None
 
     def prepare_targets(self, targets, test, device):
-        """calib / pad_size / size of every image as three small device tensors (detector_infer.py:53-58)."""
-        key = tuple(id(t) for t in targets)
-        if self._meta_cache is not None and self._meta_cache[0] == key:
-            return self._meta_cache[1]
-        calib, pad, size = [], [], []
+        """calib / pad_size / size of every image as three small device tensors (detector_infer.py:53-58). The host-side
+        scalars (calibration, image size) are cached BY VALUE; pad_size is stacked on the device like the reference
+        does, so a CUDA `pad_size` field costs no host sync."""
+        calib, size = [], []
         for t in targets:
             c = t.get_field("calib")
-            calib.append([float(c.f_u), float(c.f_v), float(c.c_u), float(c.c_v), float(c.b_x), float(c.b_y)])
-            p = t.get_field("pad_size")
-            pad.append([float(p[0]), float(p[1])])
-            size.append([float(t.size[0]), float(t.size[1])])
-        out = tuple(torch.tensor(v, dtype=torch.float32).to(device, non_blocking=True) for v in (calib, pad, size))
-        self._meta_cache = (key, out, targets)
-        return out
+            calib.append((float(c.f_u), float(c.f_v), float(c.c_u), float(c.c_v), float(c.b_x), float(c.b_y)))
+            size.append((float(t.size[0]), float(t.size[1])))
+        key = (tuple(calib), tuple(size), str(device))
+        if self._meta_cache is None or self._meta_cache[0] != key:
+            self._meta_cache = (key, torch.tensor(calib, dtype=torch.float32).to(device),
+                                torch.tensor(size, dtype=torch.float32).to(device))
+        pad = torch.stack([torch.as_tensor(t.get_field("pad_size")) for t in targets]).to(device=device, dtype=torch.float32,
+                                                                                         non_blocking=True).view(-1, 2)
+        return self._meta_cache[1], pad, self._meta_cache[2]
 
     def launch(self, heat, reg, meta):
         """the two decode kernels (asynchronous; no host sync)"""

@@ -83,6 +83,20 @@ def test_detector_vs_reference_golden(small):
     assert (result.cpu() - res_o[0]).abs().max() <= 1e-3 * max(1.0, res_o[0].abs().max().item())
 
 
+def test_forward_async_matches_forward(small):
+    """forward_async + result() (pinned-memory read, one step late) returns the same rows as forward()."""
+    m, sd, x, tg, targets = small
+    with torch.no_grad():
+        m.heads.post_processor.det_threshold = 0.0
+        ref, eu, _ = m(x.cuda(), targets)
+        p1 = m.forward_async(x.cuda(), targets).stage()
+        p2 = m.forward_async(x.cuda(), targets).stage()
+        r1, c1 = p1.result()
+        r2, c2 = p2.result()
+    assert c1 == c2 == eu['counts']
+    assert torch.equal(r1, ref.cpu()) and torch.equal(r2, ref.cpu())
+
+
 def test_predictor_alone_from_fp32_nchw_features(small):
     """Boundary A: predictor.forward(features, targets) also accepts a plain fp32 NCHW tensor."""
     m, sd, x, tg, targets = small
