@@ -239,17 +239,27 @@ def main():
             if name == "mf_dcn_nhwc_f16":
                 _, _, b_, h_, w_, cin = a[:6]
                 return 2.0 * b_ * h_ * w_ * a[11] * 9 * cin
+            if name == "mf_head_fused":          # nbranch x (3x3 Cin->256) + the 1x1 heads (53 real output channels)
+                _, _, b_, h_, w_, cin = a[:6]
+                return 2.0 * b_ * h_ * w_ * (a[11] * 256 * 9 * cin + 53 * 256)
+            if name == "mf_conv2d_rows_f16":
+                _, b_, h_, w_, cin, _, _, _, _, kh, kw, stride, pad, cout = a[:14]
+                ho, wo = (h_ + 2 * pad - kh) // stride + 1, (w_ + 2 * pad - kw) // stride + 1
+                return 2.0 * b_ * ho * wo * cout * kh * kw * min(cin, 3 if cin == 8 else cin)
             return 0.0
         table = [{"kernel": n, "ms": m, "gflop": conv_flops(n, a) / 1e9,
                   "shape": list(a[2:6]) + ([a[13]] if n == "mf_conv2d_nhwc_f16" else [])} for n, a, m in rows]
-        head = max((r for r in table if r["kernel"] == "mf_conv2d_nhwc_f16"), key=lambda r: r["gflop"])
+        head = max(table, key=lambda r: r["gflop"])
         ach = head["gflop"] / head["ms"]                      # GFLOP/ms == TFLOP/s
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("head_conv_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("head_fused_dram_bytes_per_launch" if head["kernel"] == "mf_head_fused"
+                                              else "head_conv_dram_bytes_per_launch")
         all_tf = sum(r["gflop"] for r in table) / total
-        roofline = {"bound": "tensor", "kernel": "igemm2_kernel<128,CONV_TMA> head 3x3 64->2304 (+IABN epilogue)",
+        roofline = {"bound": "tensor", "kernel": "%s: head 9 x (3x3 64->256 + IABN) %s" % (
+                        head["kernel"], "+ 1x1 heads fused (csrc/mf_head.cu)" if head["kernel"] == "mf_head_fused"
+                        else "(csrc/mf_igemm2.cu, MODE_CONV_TMA)"),
                     "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
                     "peak_source": "%s bf16 sustained (kernel timed inside the step; fp16 operands run at the bf16 rate)"
                                    % which,

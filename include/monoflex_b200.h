@@ -66,6 +66,17 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
                        int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
                        int out_planar, int out_npar, void* y, int y_ld, void* stream);
 
+/* Fused predictor head (detector_predictor.py:121-135): `nbranch` shared-input 3x3 convs (Cin -> 256 each) + InPlaceABN
+ * (scale/shift, leaky 0.01) + the 1x1 output convs of every branch in one persistent kernel; the 256-channel hidden
+ * activations stay on chip (staged in smem as the A operand of a second tcgen05.mma) except for branches with
+ * hid_col[i] >= 0, which are also stored to `hid` [B*H*W, hid_ld] at that column (edge fusion reads them).
+ * w3_packed [nbranch*256, 9*Cin] fp16 (k = tap*Cin + c); w2_packed [nbranch*32, 256] fp16 (rows >= out_nch[i] zero);
+ * bias2 [nbranch*32]; out_ptrs[i] = fp32 NCHW base pointer of branch i's first output channel (host array of device
+ * pointers), out_ctot[i] = channel count of the tensor it points into, out_nch[i] <= 32 real channels. */
+int mf_head_fused(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w3_packed, const void* w2_packed,
+                  const float* scale, const float* shift, const float* bias2, int nbranch, void* const* out_ptrs,
+                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld, void* stream);
+
 /* Fused DCNv2 (3x3, stride 1, pad 1, dilation 1, deformable_groups 1): bilinear gather of the modulated columns straight
  * into the MMA operand tile, contraction with the packed weights, affine (+bias, BN) and activation epilogue.
  * Replaces _ext.dcn_v2_forward + BatchNorm2d + ReLU of DeformConv (dla_dcn.py:384-396; src/cuda/dcn_v2_cuda.cu:42-172,

@@ -301,6 +301,15 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
                           y_ld, MF_STREAM(stream));
 }
 
+int mf_head_fused(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w3_packed, const void* w2_packed,
+                  const float* scale, const float* shift, const float* bias2, int nbranch, void* const* out_ptrs,
+                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld, void* stream) {
+  return launch_head_fused(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(w3_packed),
+                           static_cast<const __half*>(w2_packed), scale, shift, bias2, nbranch,
+                           reinterpret_cast<float* const*>(out_ptrs), out_ctot, out_nch, hid_col, static_cast<__half*>(hid),
+                           hid_ld, MF_STREAM(stream));
+}
+
 int mf_dcn_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const float* offmask, int om_ld,
                     const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
                     int out_mode, void* y, int y_ld, void* stream) {

@@ -92,33 +92,84 @@ class _predictor(nn.Module):
         abn.running_mean = torch.cat([b[1].running_mean for b in branches])
         abn.running_var = torch.cat([b[1].running_var for b in branches])
         abn.eps = branches[0][1].eps
-        hid = P.conv(x, w_all, 1, 1, abn, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
         cls = torch.empty(B, self.num_classes, H, W, dtype=torch.float32, device=dev)
         reg = torch.empty(B, self.num_reg, H, W, dtype=torch.float32, device=dev)
+        ch0s, ch = [], 0                                    # first `reg` channel of every regression branch
+        for heads in self.reg_heads:
+            ch0s.append(ch)
+            ch += sum(h.weight.shape[0] for h in heads)
+        off_ch0 = ch0s[self.offset_index[0]] + sum(h.weight.shape[0] for h in
+                                                   list(self.reg_heads[self.offset_index[0]])[:self.offset_index[1]])
+        import os
+        fused = os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
+            all(sum(h.weight.shape[0] for h in heads) <= 32 for heads in self.reg_heads) and self.num_classes <= 32
+        if fused:
+            # ---- one kernel: 9 x (3x3 conv + IABN) + every 1x1 head; hidden activations stay on chip (csrc/mf_head.cu)
+            nb = len(branches)
+            w3, n_pad, k_pad = P.pack_weight(w_all)
+            scale, shift = P.affine(nb * hc, n_pad, abn, None, abs_weight=True)
+            head_w = torch.zeros(nb * 32, hc, dtype=torch.float32, device=dev)
+            head_bias = torch.zeros(nb * 32, dtype=torch.float32, device=dev)
+            out_ptrs, out_ctot, out_nch, hid_col = [], [], [], []
+            head_lists = [[self.class_head[2]]] + [list(h) for h in self.reg_heads]
+            for i, heads in enumerate(head_lists):
+                wcat = torch.cat([h.weight.detach().float().reshape(h.weight.shape[0], hc) for h in heads], 0)
+                bcat = torch.cat([h.bias.detach().float() for h in heads])
+                head_w[i * 32:i * 32 + wcat.shape[0]] = wcat
+                head_bias[i * 32:i * 32 + bcat.shape[0]] = bcat
+                out_nch.append(wcat.shape[0])
+                if i == 0:
+                    out_ptrs.append(cls.data_ptr()); out_ctot.append(self.num_classes)
+                else:
+                    out_ptrs.append(reg.data_ptr() + 4 * ch0s[i - 1] * H * W); out_ctot.append(self.num_reg)
+                hid_col.append(-1)
+            hid_ld = 2 * hc
+            hid_buf = torch.zeros(B * H * W, hid_ld, dtype=torch.half, device=dev)
+            hid_col[0] = 0                                   # edge fusion reads the cls branch ...
+            oi = self.offset_index[0] + 1
+            hid_col[oi] = hc                                 # ... and the 3d_offset branch
+            w2h = head_w.half().contiguous()
+            import ctypes
+            arr_p = (ctypes.c_void_p * nb)(*out_ptrs)
+            arr_ct, arr_nc, arr_hc = (ctypes.c_int * nb)(*out_ctot), (ctypes.c_int * nb)(*out_nch), (ctypes.c_int * nb)(*hid_col)
+            P.keep.extend([w2h, head_bias, hid_buf, arr_p, arr_ct, arr_nc, arr_hc, cls, reg])
+            cin = feat.C
+            P.add("mf_head_fused", lambda: (
+                x.ptr(), x.ld, B, H, W, cin, w3.data_ptr(), w2h.data_ptr(), scale.data_ptr(), shift.data_ptr(), head_bias.data_ptr(),
+                nb, ctypes.cast(arr_p, ctypes.c_void_p), ctypes.cast(arr_ct, ctypes.c_void_p),
+                ctypes.cast(arr_nc, ctypes.c_void_p), ctypes.cast(arr_hc, ctypes.c_void_p), hid_buf.data_ptr(), hid_ld))
 
-        def slice_of(i):
-            s = P.act(B, H, W, hc)
-            s.owner, s.ch_off = hid, i * hc
-            return s
-        P.conv_to_f32(slice_of(0), self.class_head[2].weight, self.class_head[2].bias, cls, engine.OUT_F32_NCHW,
-                      engine.ACT_NONE, self.num_classes)
-        ch = 0
-        for i, heads in enumerate(self.reg_heads):
-            src = slice_of(i + 1)
-            for head in heads:
-                P.conv_to_f32(src, head.weight, head.bias, reg[:, ch:], engine.OUT_F32_NCHW, engine.ACT_NONE, self.num_reg)
-                if self.enable_edge_fusion and [i, list(heads).index(head)] == self.offset_index:
-                    off_ch0 = ch
-                ch += head.weight.shape[0]
+            class _Hid(object):
+                pass
+            hid = _Hid()
+            hid.ptr = lambda: hid_buf.data_ptr()
+            hid.ld = hid_ld
+            edge_cols = (0, hc)
+        else:
+            hid = P.conv(x, w_all, 1, 1, abn, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
+
+            def slice_of(i):
+                sl = P.act(B, H, W, hc)
+                sl.owner, sl.ch_off = hid, i * hc
+                return sl
+            P.conv_to_f32(slice_of(0), self.class_head[2].weight, self.class_head[2].bias, cls, engine.OUT_F32_NCHW,
+                          engine.ACT_NONE, self.num_classes)
+            ch = 0
+            for i, heads in enumerate(self.reg_heads):
+                src = slice_of(i + 1)
+                for head in heads:
+                    P.conv_to_f32(src, head.weight, head.bias, reg[:, ch:], engine.OUT_F32_NCHW, engine.ACT_NONE,
+                                  self.num_reg)
+                    ch += head.weight.shape[0]
+            edge_cols = (0, (self.offset_index[0] + 1) * hc)
         P.edge_idx = torch.zeros(B, K_edge, 2, dtype=torch.long, device=dev)
         P.edge_len = torch.zeros(B, dtype=torch.long, device=dev)
         if self.enable_edge_fusion:
             ea = P.act(B, 1, K_edge + 2, hc)
             eb = P.act(B, 1, K_edge + 2, hc)
-            oi = self.offset_index[0] + 1
             ow, oh = self.output_width, self.output_height
-            P.add("mf_edge_gather", lambda: (hid.ptr(), hid.ld, 0, oi * hc, P.edge_idx.data_ptr(), ea.ptr(), eb.ptr(), B,
-                                              H, W, K_edge, ow, oh))
+            P.add("mf_edge_gather", lambda: (hid.ptr(), hid.ld, edge_cols[0], edge_cols[1], P.edge_idx.data_ptr(), ea.ptr(),
+                                              eb.ptr(), B, H, W, K_edge, ow, oh))
             for src, seq, dst, ch0, ctot in ((ea, self.trunc_heatmap_conv, cls, 0, self.num_classes),
                                              (eb, self.trunc_offset_conv, reg, off_ch0, self.num_reg)):
                 t = P.conv(src, seq[0].weight, 1, 0, seq[1], bias=seq[0].bias, act=engine.ACT_NONE)   # [B,1,K,256]
