@@ -110,7 +110,7 @@ def main():
     config = {"workload": "DLA-34+DCNv2+heads+decode inference, batch %d/GPU, 384x1280 synthetic, %dxB200 (BASELINE configs[1]; --batch 32 = configs[3])"
               % (args.batch, args.gpus), "batch_per_gpu": args.batch, "height": H, "width": W,
               "parallelism": "replicas x%d (images shard across GPUs, no data-path collective)" % args.gpus,
-              "l2": "4 rotating input batches (189 MB) + 2.9 GB activation working set >> 126 MB L2"}
+              "l2": "4 rotating input batches (189 MB) + ~1.8 GB activation working set >> 126 MB L2"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -110,6 +110,20 @@ int mf_edge_head_add(const void* t, const float* w, const float* bias, int n_out
 int mf_sigmoid_clamp(float* x, long long n, void* stream);
 /* FocalLoss.forward (model/layers/focal_loss.py:35-55): out2[0] = loss sum, out2[1] = num_pos */
 int mf_focal_loss_forward(const float* pred, const float* target, long long n, float* out2, void* stream);
+/* autograd of the above: grad_pred[i] = scale[0] * dLoss/dpred[i]; scale is a DEVICE scalar
+ * (loss weight / clamp(num_pos, 1), model/head/detector_loss.py:276) so the step needs no host sync */
+int mf_focal_loss_backward(const float* pred, const float* target, long long n, const float* scale, float* grad_pred,
+                           void* stream);
+
+/* torch.optim.AdamW as configured by solver/__init__.py:10-37 (one param group per tensor, lr x BIAS_LR_FACTOR for
+ * "bias" tensors, betas (0.9, 0.99), weight decay 1e-5) over ONE flat fp32 arena: every tensor starts at a multiple of
+ * mf_adamw_chunk() elements and chunk_lr[n_chunks] (device) holds its group's lr (0 = padding / frozen). step is the
+ * 1-based update count; grads are multiplied by grad_scale first (1/world_size after an NCCL SUM of the arena);
+ * lr_scale is the scheduler's multiplier (solver/__init__.py:64-92). One launch, 28 B per parameter. */
+int mf_adamw_chunk(void);
+int mf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* chunk_lr,
+                  long long n_chunks, float beta1, float beta2, float eps, float weight_decay, long long step,
+                  float grad_scale, float lr_scale, void* stream);
 
 /* nms_hm alone (model/layers/utils.py:45-58): out = heat * (maxpool3x3(heat) == heat), planes = B*C */
 int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream);

@@ -359,6 +359,17 @@ int mf_sigmoid_clamp(float* x, long long n, void* stream) { return launch_sigmoi
 int mf_focal_loss_forward(const float* pred, const float* target, long long n, float* out2, void* stream) {
   return launch_focal_loss(pred, target, n, out2, MF_STREAM(stream));
 }
+int mf_focal_loss_backward(const float* pred, const float* target, long long n, const float* scale, float* grad_pred,
+                           void* stream) {
+  return launch_focal_loss_backward(pred, target, n, scale, grad_pred, MF_STREAM(stream));
+}
+int mf_adamw_chunk(void) { return MF_ADAMW_CHUNK; }
+int mf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* chunk_lr,
+                  long long n_chunks, float beta1, float beta2, float eps, float weight_decay, long long step,
+                  float grad_scale, float lr_scale, void* stream) {
+  return launch_adamw_arena(params, grads, exp_avg, exp_avg_sq, chunk_lr, n_chunks, beta1, beta2, eps, weight_decay, step,
+                            grad_scale, lr_scale, MF_STREAM(stream));
+}
 int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream) {
   return launch_nms_hm(heat, out, planes, H, W, MF_STREAM(stream));
 }

@@ -18,6 +18,12 @@ int launch_edge_head_add(const __half* t, const float* w, const float* bias, int
                          cudaStream_t st);
 int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st);
 int launch_focal_loss(const float* pred, const float* tgt, long long n, float* out2, cudaStream_t st);
+#define MF_ADAMW_CHUNK 512   /* arena granularity (elements) of the per-chunk lr table */
+int launch_focal_loss_backward(const float* pred, const float* tgt, long long n, const float* scale, float* grad,
+                               cudaStream_t st);
+int launch_adamw_arena(float* p, const float* g, float* m, float* v, const float* chunk_lr, long long n_chunks,
+                       float beta1, float beta2, float eps, float wd, long long step, float grad_scale, float lr_scale,
+                       cudaStream_t st);
 int launch_decode(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
                   const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
                   float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,

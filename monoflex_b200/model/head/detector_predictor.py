@@ -98,8 +98,10 @@ class _predictor(nn.Module):
         for heads in self.reg_heads:
             ch0s.append(ch)
             ch += sum(h.weight.shape[0] for h in heads)
-        off_ch0 = ch0s[self.offset_index[0]] + sum(h.weight.shape[0] for h in
-                                                   list(self.reg_heads[self.offset_index[0]])[:self.offset_index[1]])
+        off_ch0 = 0
+        if self.enable_edge_fusion:
+            off_ch0 = ch0s[self.offset_index[0]] + sum(h.weight.shape[0] for h in
+                                                       list(self.reg_heads[self.offset_index[0]])[:self.offset_index[1]])
         import os
         fused = os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
             all(sum(h.weight.shape[0] for h in heads) <= 32 for heads in self.reg_heads) and self.num_classes <= 32
@@ -125,9 +127,9 @@ class _predictor(nn.Module):
                 hid_col.append(-1)
             hid_ld = 2 * hc
             hid_buf = torch.zeros(B * H * W, hid_ld, dtype=torch.half, device=dev)
-            hid_col[0] = 0                                   # edge fusion reads the cls branch ...
-            oi = self.offset_index[0] + 1
-            hid_col[oi] = hc                                 # ... and the 3d_offset branch
+            if self.enable_edge_fusion:
+                hid_col[0] = 0                               # edge fusion reads the cls branch ...
+                hid_col[self.offset_index[0] + 1] = hc       # ... and the 3d_offset branch
             w2h = head_w.half().contiguous()
             import ctypes
             arr_p = (ctypes.c_void_p * nb)(*out_ptrs)

@@ -19,11 +19,11 @@ for k,a in sorted(agg.items(), key=lambda kv:-kv[1][1])[:40]:
     print("%-28s %-28s n=%2d ms=%7.3f gflop=%8.1f TF/s=%6.1f" % (k[0], k[1], a[0], a[1], a[2], a[2]/a[1] if a[1] else 0))
 PY
 if [ -n "$NCU_LIST" ]; then
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"igemm|maxpool|upsample|edge_|nms_|topk_|pack_image|sigmoid" -c 700 --csv --log-file gpurun_out/launches_ncu_$R.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$R.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"igemm|maxpool|upsample|edge_|nms_|topk_|pack_image|sigmoid|head_fused|rows_conv" -c 700 --csv --log-file gpurun_out/launches_ncu_$R.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$R.log 2>&1
 echo "ncu list rc $?"
 fi
 if [ -n "$NCU_FULL" ]; then
-timeout 600 ncu --set full --kernel-name regex:"igemm|nms_|topk_" --clock-control none --import-source on --profile-from-start off -f -o /tmp/prof_$R python tools/profile_kernels.py > gpurun_out/ncu_full_$R.log 2>&1
+timeout 600 ncu --set full --kernel-name regex:"igemm|nms_|topk_|head_fused|rows_conv" --clock-control none --import-source on --profile-from-start off -f -o /tmp/prof_$R python tools/profile_kernels.py > gpurun_out/ncu_full_$R.log 2>&1
 echo "ncu full rc $?"; tail -3 gpurun_out/ncu_full_$R.log
 ncu -i /tmp/prof_$R.ncu-rep --page raw --csv > gpurun_out/prof_raw_$R.csv 2>/dev/null
 ncu -i /tmp/prof_$R.ncu-rep --page details --csv > gpurun_out/prof_details_$R.csv 2>/dev/null

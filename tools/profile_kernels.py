@@ -35,7 +35,7 @@ def pick(plan, name, pred):
 
 
 sel_spec = [
-    ("head", hp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 2304),
+    ("head", hp, "mf_head_fused", lambda a: True),
     ("dcn64", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 64 and a[3] == 96),
     ("dcn128", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 128 and a[3] == 48),
     ("offconv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 27 and a[5] == 64 and a[3] == 96),

@@ -59,7 +59,8 @@ for n, r in enumerate(rows[2:]):
             i = hdr.index(k)
             out.append('   %-92s %s %s' % (k, r[i], units[i]))
     if n == 0:
-        traffic['head_conv_dram_bytes_per_launch'] = val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')
+        key = 'head_fused_dram_bytes_per_launch' if 'head_fused' in kn else 'head_conv_dram_bytes_per_launch'
+        traffic[key] = val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')
 open('profiles/ncu_full_summary_%s.txt' % R, 'w').write('\n'.join(out) + '\n')
 json.dump(traffic, open('profiles/roofline_traffic.json', 'w'), indent=1)
 for f in ('bench_%s.json', 'bench_ref_%s.json', 'launches_events_%s.json', 'clocks_%s.csv', 'pytest_gpu_%s.log', 'smoke_%s.log'):
