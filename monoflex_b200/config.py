@@ -23,4 +23,7 @@ def default_cfg(width=1280, height=384, device="cuda"):
     cfg.DATASETS = NS(DETECT_CLASSES=("Car", "Pedestrian", "Cyclist"), TEST_SPLIT="test", MAX_OBJECTS=40)
     cfg.TEST = NS(DETECTIONS_THRESHOLD=0.2, DETECTIONS_PER_IMG=50, UNCERTAINTY_AS_CONFIDENCE=True, PRED_2D=True,
                   EVAL_DIS_IOUS=False, EVAL_DEPTH=False)
+    # runs/monoflex.yaml:61-78 over config/defaults.py:252-299
+    cfg.SOLVER = NS(OPTIMIZER="adamw", BASE_LR=3e-4, WEIGHT_DECAY=1e-5, BIAS_LR_FACTOR=2.0, STEPS=(20000, 25000),
+                    LR_DECAY=0.1, LR_CLIP=1e-7, LR_WARMUP=False, GRAD_NORM_CLIP=-1, IMS_PER_BATCH=8)
     return cfg
