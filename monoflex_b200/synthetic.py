@@ -222,3 +222,176 @@ def make_param_lists(tg):
         t.add_field('edge_len', tg['edge_len'][b])
         out.append(t)
     return out
+
+
+# ------------------------------------------------------------------------------------------- training targets (row R12)
+DIM_MEAN = ((3.8840, 1.5261, 1.6286), (0.8423, 1.7607, 0.6602), (1.7635, 1.7372, 0.5968))   # config/defaults.py:206-208
+MAX_OBJECTS = 40                                                                             # config/defaults.py DATASETS.MAX_OBJECTS
+ALPHA_CENTERS = (0.0, math.pi / 2, math.pi, -math.pi / 2)                                    # kitti.py:75
+
+
+def _project(P, pts):
+    """rect-camera points [n,3] -> pixel (u, v) with the 3x4 projection matrix (kitti_utils.py project_rect_to_image)."""
+    h = np.concatenate([pts, np.ones((pts.shape[0], 1))], axis=1) @ np.asarray(P, dtype=np.float64).T
+    return h[:, :2] / h[:, 2:3]
+
+
+def _gaussian(hm, cx, cy, rx, ry):
+    """umich gaussian splat with independent radii (data/datasets/kitti_utils.py draw_umich_gaussian[_2D] semantics:
+    sigma = (2r+1)/6 per axis, element-wise max with what is already there)."""
+    H, W = hm.shape
+    sx, sy = (2 * rx + 1) / 6.0, (2 * ry + 1) / 6.0
+    x0, x1, y0, y1 = max(0, cx - rx), min(W - 1, cx + rx), max(0, cy - ry), min(H - 1, cy + ry)
+    ys, xs = np.mgrid[y0:y1 + 1, x0:x1 + 1]
+    g = np.exp(-((xs - cx) ** 2) / (2 * sx * sx) - ((ys - cy) ** 2) / (2 * sy * sy)).astype(np.float32)
+    hm[y0:y1 + 1, x0:x1 + 1] = np.maximum(hm[y0:y1 + 1, x0:x1 + 1], g)
+    hm[cy, cx] = 1.0
+
+
+def make_train_targets(batch, seed=5, out_w=320, out_h=96, max_objs=MAX_OBJECTS, empty_image=1):
+    """Synthetic per-image TRAINING target fields with the shapes, dtypes and encodings of KITTIDataset.__getitem__
+    (data/datasets/kitti.py:296-521): objects are sampled in 3D (class-mean dimensions, depth 4-60 m, random yaw),
+    projected with KITTI_P2, and encoded exactly like the reference encodes labels (projected centre, truncated centres
+    moved to the image border, 10 keypoints relative to the integer centre with visibility, multi-bin orientation, ...).
+    Image `empty_image` (if < batch) gets no object: the reference indexes calibrations by RANK among non-empty images in
+    decode_depth_from_keypoints_batch (anno_encoder.py:186), which only shows with an empty image in the batch.
+    Returns a list of dicts of numpy arrays (one per image)."""
+    g = _rng(seed)
+    img_w, img_h = out_w * 4 - 2 * PAD_SIZE[0], out_h * 4 - 2 * PAD_SIZE[1]
+    pad = np.asarray(PAD_SIZE, dtype=np.float64)
+    x_min, y_min = math.ceil(PAD_SIZE[0] / 4), math.ceil(PAD_SIZE[1] / 4)
+    x_max, y_max = (PAD_SIZE[0] + img_w - 1) // 4, (PAD_SIZE[1] + img_h - 1) // 4
+    P = np.asarray(KITTI_P2, dtype=np.float64)
+    out = []
+    for b in range(batch):
+        f = dict(hm=np.zeros((NUM_CLASSES, out_h, out_w), np.float32), cls_ids=np.zeros(max_objs, np.int32),
+                 target_centers=np.zeros((max_objs, 2), np.int32), bboxes=np.zeros((max_objs, 4), np.float32),
+                 keypoints=np.zeros((max_objs, 10, 3), np.float32), keypoints_depth_mask=np.zeros((max_objs, 3), np.float32),
+                 dimensions=np.zeros((max_objs, 3), np.float32), locations=np.zeros((max_objs, 3), np.float32),
+                 rotys=np.zeros(max_objs, np.float32), alphas=np.zeros(max_objs, np.float32),
+                 offset_3D=np.zeros((max_objs, 2), np.float32), orientations=np.zeros((max_objs, 8), np.float32),
+                 reg_mask=np.zeros(max_objs, np.uint8), trunc_mask=np.zeros(max_objs, np.uint8),
+                 reg_weight=np.zeros(max_objs, np.float32), pad_size=np.asarray(PAD_SIZE, np.float32),
+                 ori_img=np.zeros((1,), np.float32))
+        n_obj = 0 if b == empty_image else int(g.integers(3, 14))
+        i = 0
+        for _ in range(n_obj * 3):
+            if i >= n_obj:
+                break
+            cls = int(g.choice(3, p=[0.7, 0.15, 0.15]))
+            l, h, w = (np.asarray(DIM_MEAN[cls]) * g.uniform(0.85, 1.15, 3))
+            z = float(g.uniform(4.0, 60.0))
+            x = float(g.uniform(-0.98, 0.98)) * z                     # beyond ~0.84 z the centre leaves the image: truncated
+            yb = 1.65 + float(g.normal(0, 0.15))                      # bottom-face height in camera coordinates (y down)
+            ry = float(g.uniform(-math.pi, math.pi))
+            loc = np.array([x, yb - h / 2, z])                        # kitti.py:352-353: centre of the box
+            c, s = math.cos(ry), math.sin(ry)
+            xc = np.array([l, l, -l, -l, l, l, -l, -l]) / 2
+            yc = np.array([0, 0, 0, 0, -h, -h, -h, -h])
+            zc = np.array([w, -w, -w, w, w, -w, -w, w]) / 2
+            corners = np.stack([c * xc + s * zc + x, yc + yb, -s * xc + c * zc + z], axis=1)   # object3d generate_corners3d
+            if corners[:, 2].min() <= 0.5:
+                continue
+            c2 = _project(P, corners)
+            box = np.array([c2[:, 0].min(), c2[:, 1].min(), c2[:, 0].max(), c2[:, 1].max()])
+            box = np.array([max(box[0], 0), max(box[1], 0), min(box[2], img_w - 1), min(box[3], img_h - 1)])
+            if box[2] - box[0] < 4 or box[3] - box[1] < 4:
+                continue
+            pc = _project(P, loc[None])[0]
+            inside = (0 <= pc[0] <= img_w - 1) and (0 <= pc[1] <= img_h - 1)
+            tpc = pc.copy()
+            if not inside:                                            # kitti.py:372-381 / approx_proj_center 'intersect'
+                c2d = (box[:2] + box[2:]) / 2
+                d = pc - c2d
+                ts = [1.0]
+                for k, lim in ((0, img_w - 1), (1, img_h - 1)):
+                    if d[k] > 0:
+                        ts.append((lim - c2d[k]) / d[k])
+                    elif d[k] < 0:
+                        ts.append((0 - c2d[k]) / d[k])
+                tpc = c2d + d * max(0.0, min(ts))
+            kp3 = np.concatenate([corners, corners[:4].mean(0, keepdims=True), corners[4:].mean(0, keepdims=True)], 0)
+            kp2 = _project(P, kp3)
+            vis = (kp2[:, 0] >= 0) & (kp2[:, 0] <= img_w - 1) & (kp2[:, 1] >= 0) & (kp2[:, 1] <= img_h - 1) & (kp3[:, 2] > 0)
+            vis = np.append(np.tile(vis[:4] | vis[4:8], 2), np.tile(vis[8] | vis[9], 2))        # kitti.py:397-399
+            dvalid = np.stack((vis[[8, 9]].all(), vis[[0, 2, 4, 6]].all(), vis[[1, 3, 5, 7]].all())).astype(np.float32)
+            kp2 = (kp2 + pad) / 4
+            tpc, pcf = (tpc + pad) / 4, (pc + pad) / 4
+            boxf = (box + np.tile(pad, 2)) / 4
+            tc = np.round(tpc).astype(np.int64)
+            tc[0], tc[1] = min(max(tc[0], x_min), x_max), min(max(tc[1], y_min), y_max)
+            pred_2d = boxf[0] <= tc[0] <= boxf[2] and boxf[1] <= tc[1] <= boxf[3] and g.uniform() > 0.08   # + some 'wrong annotations'
+            bw, bh = boxf[2] - boxf[0], boxf[3] - boxf[1]
+            if not inside:                                            # kitti.py:428-433 (edge heat map: 1-D gaussian)
+                rx = max(0, int(min(tc[0] - boxf[0], boxf[2] - tc[0]) * 0.5))
+                ryy = max(0, int(min(tc[1] - boxf[1], boxf[3] - tc[1]) * 0.5))
+                if min(rx, ryy) > 0:
+                    rx = 0
+                _gaussian(f["hm"][cls], int(tc[0]), int(tc[1]), rx, ryy)
+            else:
+                r = max(0, int(0.3 * min(bw, bh)))
+                _gaussian(f["hm"][cls], int(tc[0]), int(tc[1]), r, r)
+            alpha = ry - math.atan2(x, z)
+            alpha = (alpha + math.pi) % (2 * math.pi) - math.pi
+            f["cls_ids"][i] = cls
+            f["target_centers"][i] = tc
+            f["offset_3D"][i] = pcf - tc
+            if pred_2d:
+                f["bboxes"][i] = boxf
+            f["keypoints"][i] = np.concatenate([kp2 - tc[None].astype(np.float64), vis[:, None].astype(np.float64)], 1)
+            f["keypoints_depth_mask"][i] = dvalid
+            f["dimensions"][i] = (l, h, w)
+            f["locations"][i] = loc
+            f["rotys"][i], f["alphas"][i] = ry, alpha
+            enc = np.zeros(8)                                          # kitti.py:181-200 encode_alpha_multibin(num_bin=4)
+            offs = alpha - np.asarray(ALPHA_CENTERS)
+            offs[offs > math.pi] -= 2 * math.pi
+            offs[offs < -math.pi] += 2 * math.pi
+            for k in range(4):
+                if abs(offs[k]) < math.pi / 4 + math.pi / 12:
+                    enc[k], enc[4 + k] = 1, offs[k]
+            f["orientations"][i] = enc
+            f["reg_mask"][i], f["reg_weight"][i], f["trunc_mask"][i] = 1, 1, int(not inside)
+            i += 1
+        out.append(f)
+    return out
+
+
+def make_train_param_lists(fields):
+    """ParamsList objects (is_train=True) as the reference's collate hands them to model(images, targets)
+    (data/collate_batch.py); field names of kitti.py:496-521."""
+    from .structures import Calibration, ParamsList
+    idx, n, img_size = edge_indices()
+    res = []
+    for f in fields:
+        t = ParamsList((1280, 384), is_train=True)
+        for k, v in f.items():
+            t.add_field("2d_bboxes" if k == "bboxes" else k, torch.from_numpy(np.ascontiguousarray(v)))
+        t.add_field("calib", Calibration(KITTI_P2))
+        t.add_field("edge_indices", idx)
+        t.add_field("edge_len", torch.tensor(n, dtype=torch.long))
+        res.append(t)
+    return res
+
+
+def make_train_predictions(batch, fields, seed=6, out_w=320, out_h=96):
+    """Predictor outputs for loss tests: `cls` = a valid heat map in (1e-4, 1-1e-4) (sigmoid_hm already applied,
+    detector_predictor.py:163), `reg` ~ N(0, 0.5) with the regression vector at every object centre nudged towards the
+    label so that all loss branches (valid / invalid key-point depths, every orientation bin) see sane magnitudes."""
+    g = _rng(seed)
+    logits = g.standard_normal((batch, NUM_CLASSES, out_h, out_w)) * 1.5 - 3.0
+    cls = np.clip(1.0 / (1.0 + np.exp(-logits)), 1e-4, 1 - 1e-4).astype(np.float32)
+    reg = (g.standard_normal((batch, 50, out_h, out_w)) * 0.5).astype(np.float32)
+    for b, f in enumerate(fields):
+        for i in np.nonzero(f["reg_mask"])[0]:
+            x, y = f["target_centers"][i]
+            kp = f["keypoints"][i, :, :2].reshape(-1)
+            reg[b, 6:26, y, x] = kp + g.standard_normal(20).astype(np.float32) * 0.3
+            reg[b, 4:6, y, x] = f["offset_3D"][i] + g.standard_normal(2).astype(np.float32) * 0.1
+            bx = f["bboxes"][i]
+            if bx[2] > bx[0]:
+                reg[b, 0:4, y, x] = np.array([x - bx[0], y - bx[1], bx[2] - x, bx[3] - y]) * g.uniform(0.7, 1.3, 4)
+            reg[b, 29:32, y, x] = g.standard_normal(3).astype(np.float32) * 0.1
+            z = f["locations"][i, 2] * float(np.exp(g.normal(0, 0.1)))
+            reg[b, 48, y, x] = -math.log(z)                              # 1/sigmoid(v) - 1 = exp(-v) = z
+    return torch.from_numpy(cls), torch.from_numpy(reg)

@@ -369,3 +369,177 @@ def focal_loss(pred, target, alpha=2, beta=4):
     pl = (torch.log(pred) * torch.pow(1 - pred, alpha) * pos).sum()
     nl = (torch.log(1 - pred) * torch.pow(pred, alpha) * torch.pow(1 - target, beta) * neg).sum()
     return -nl - pl, pos.sum()
+
+
+# ------------------------------------------------------------------------------------------------ 11-term loss (row R12)
+LOSS_NAMES = ['hm_loss', 'bbox_loss', 'depth_loss', 'offset_loss', 'orien_loss', 'dims_loss', 'corner_loss',
+              'keypoint_loss', 'keypoint_depth_loss', 'trunc_offset_loss', 'weighted_avg_depth_loss']   # runs/monoflex.yaml:45
+LOSS_WEIGHTS = dict(zip(LOSS_NAMES, [1, 1, 1, 0.5, 1, 1, 0.2, 1.0, 0.2, 0.1, 0.2]))                   # runs/monoflex.yaml:47
+UNC_RANGE = (-10.0, 10.0)                                                                              # config/defaults.py:162
+
+
+def encode_box3d(rotys, dims, locs):
+    """Anno_Encoder.encode_box3d anno_encoder.py:88-122: 8 corners [N,8,3] of boxes (l,h,w) rotated by ry about y."""
+    N = rotys.shape[0]
+    l, h, w = dims[:, 0:1] * 0.5, dims[:, 1:2] * 0.5, dims[:, 2:3] * 0.5
+    sx = torch.tensor([-1., -1, 1, 1, -1, -1, 1, 1])          # index row [4,5,0,1,6,7,2,3] of the +/- half-extent table
+    sy = torch.tensor([1., 1, 1, 1, -1, -1, -1, -1])          # [0..7]
+    sz = torch.tensor([-1., 1, 1, -1, -1, 1, 1, -1])          # [4,0,1,5,6,2,3,7]
+    X, Y, Z = l * sx, h * sy, w * sz
+    c, s = rotys.cos().view(N, 1), rotys.sin().view(N, 1)
+    bx = c * X + s * Z + locs[:, 0:1]
+    by = Y + locs[:, 1:2]
+    bz = -s * X + c * Z + locs[:, 2:3]
+    return torch.stack([bx, by, bz], 2)
+
+
+def giou_loss(pred, target):
+    """IOULoss('giou').forward layers/iou_loss.py:12-49 -> (1 - giou, iou)."""
+    pl, pt, pr, pb = pred.unbind(1)
+    tl, tt, tr, tb = target.unbind(1)
+    t_area, p_area = (tl + tr) * (tt + tb), (pl + pr) * (pt + pb)
+    w_i = torch.min(pl, tl) + torch.min(pr, tr)
+    gw = torch.max(pl, tl) + torch.max(pr, tr)
+    h_i = torch.min(pb, tb) + torch.min(pt, tt)
+    gh = torch.max(pb, tb) + torch.max(pt, tt)
+    ac = gw * gh + 1e-7
+    inter = w_i * h_i
+    union = t_area + p_area - inter
+    ious = (inter + 1.0) / (union + 1.0)
+    return 1 - (ious - (ac - union) / ac), ious
+
+
+def multibin_loss(vec, gt, num_bin=4):
+    """Real_MultiBin_loss detector_loss.py:495-517."""
+    cls_losses, reg_losses, reg_cnt = 0, 0, 0
+    for i in range(num_bin):
+        cls_losses = cls_losses + F.cross_entropy(vec[:, 2 * i:2 * i + 2], gt[:, i].long(), reduction='none').mean()
+        m = gt[:, i] == 1
+        if m.sum() > 0:
+            s = num_bin * 2 + i * 2
+            po = F.normalize(vec[m, s:s + 2])
+            reg = (po[:, 0] - torch.sin(gt[m, num_bin + i])).abs() + (po[:, 1] - torch.cos(gt[m, num_bin + i])).abs()
+            reg_losses = reg_losses + reg.sum()
+            reg_cnt = reg_cnt + m.sum()
+    return cls_losses / num_bin + reg_losses / reg_cnt
+
+
+def loss_computation(pred_cls, pred_reg, fields, calibs_P, down_ratio=4):
+    """Loss_Computation.__call__ detector_loss.py:267-493 with prepare_targets :88-114 and prepare_predictions :116-265 for
+    the runs/monoflex.yaml configuration (L1 regression, giou, L1 depth with uncertainty, multi-bin, soft_combine corner
+    depth, 'log' truncation offset loss, MODIFY_INVALID_KEYPOINT_DEPTH). `fields`: list (per image) of dicts of tensors
+    named like the ParamsList fields; `pred_cls` is the sigmoid-ed, clamped heat map. Returns (loss_dict, log_dict) of
+    tensors; every entry of loss_dict is differentiable w.r.t. pred_cls / pred_reg. The shapely '3D_IoU' logging metric
+    (:333) is not restated (SURVEY §8c iii)."""
+    B, C, H, W = pred_reg.shape
+    st = lambda k: torch.stack([torch.as_tensor(f[k]) for f in fields])
+    hm = st('hm').float()
+    reg_mask = st('reg_mask').view(-1).bool()
+    M = st('reg_mask').shape[1]
+    batch_idxs = torch.arange(B).view(-1, 1).expand(B, M).reshape(-1)[reg_mask]
+    centers = st('target_centers')
+    pts = centers.view(-1, 2)[reg_mask]                                   # int
+    box = st('bboxes').view(-1, 4)[reg_mask].float()
+    t_h, t_w = box[:, 3] - box[:, 1], box[:, 2] - box[:, 0]
+    t_reg2d = torch.cat((pts - box[:, :2], box[:, 2:] - pts), 1)
+    m2d = (t_h > 0) & (t_w > 0)
+    t_reg2d = t_reg2d[m2d]
+    t_cls = st('cls_ids').view(-1)[reg_mask].long()
+    t_depth = st('locations')[..., -1].reshape(-1)[reg_mask].float()
+    t_roty = st('rotys').view(-1)[reg_mask].float()
+    t_off = st('offset_3D').view(-1, 2)[reg_mask].float()
+    t_dims = st('dimensions').view(-1, 3)[reg_mask].float()
+    t_ori = st('orientations').view(-1, 8)[reg_mask].float()
+    pads = st('pad_size').float()
+    calibs = [calib_from_P(P) for P in calibs_P]
+
+    def unproject(points, offsets, depths):                               # decode_location_flatten anno_encoder.py:142-155
+        uv = (points + offsets) * down_ratio - pads[batch_idxs]
+        cu = torch.tensor([calibs[int(b)]['c_u'] for b in batch_idxs]); cv = torch.tensor([calibs[int(b)]['c_v'] for b in batch_idxs])
+        fu = torch.tensor([calibs[int(b)]['f_u'] for b in batch_idxs]); fv = torch.tensor([calibs[int(b)]['f_v'] for b in batch_idxs])
+        bx = torch.tensor([calibs[int(b)]['b_x'] for b in batch_idxs]); by = torch.tensor([calibs[int(b)]['b_y'] for b in batch_idxs])
+        x = ((uv[:, 0] - cu) * depths) / fu + bx
+        y = ((uv[:, 1] - cv) * depths) / fv + by
+        return torch.stack([x, y, depths], 1)
+
+    t_loc = unproject(pts, t_off, t_depth)
+    t_corners = encode_box3d(t_roty, t_dims, t_loc)
+    trunc = st('trunc_mask').view(-1)[reg_mask].bool()
+
+    # predictions at the object centres (select_point_of_interest layers/utils.py:120-145)
+    idx = (centers[..., 1].long() * W + centers[..., 0].long())           # [B, M]
+    pois = pred_reg.view(B, C, H * W).permute(0, 2, 1).gather(1, idx.unsqueeze(-1).expand(B, M, C)).reshape(-1, C)[reg_mask]
+    p_reg2d = F.relu(pois[m2d][:, key2channel('2d_dim')])
+    p_off = pois[:, key2channel('3d_offset')]
+    p_dims = pois[:, key2channel('3d_dim')].exp() * torch.tensor(DIM_MEAN)[t_cls]
+    p_ori = torch.cat((pois[:, key2channel('ori_cls')], pois[:, key2channel('ori_offset')]), 1)
+    p_depth = (1 / torch.sigmoid(pois[:, key2channel('depth')].squeeze(-1)) - 1).clamp(0.1, 100)
+    p_dunc = pois[:, key2channel('depth_uncertainty')].squeeze(-1).clamp(*UNC_RANGE)
+    kpt = st('keypoints').view(B * M, -1, 3)[reg_mask].float()
+    t_kp, t_kpm = kpt[..., :2], kpt[..., 2]
+    t_kdm = st('keypoints_depth_mask').view(-1, 3)[reg_mask].bool()
+    p_kp = pois[:, key2channel('corner_offset')].reshape(-1, 10, 2)
+    # decode_depth_from_keypoints_batch anno_encoder.py:174-206 -- NB calib = calibs[idx] with idx the RANK of the image
+    # among the images that have objects (enumerate over unique batch indices), not the image index itself
+    ranks = {int(g): r for r, g in enumerate(torch.unique(batch_idxs, sorted=True).tolist())}
+    fu_kp = torch.tensor([calibs[0 if B == 1 else ranks[int(b)]]['f_u'] for b in batch_idxs])
+    h3d = p_dims[:, 1]
+    ch = p_kp[:, -2, 1] - p_kp[:, -1, 1]
+    c02 = p_kp[:, [0, 2], 1] - p_kp[:, [4, 6], 1]
+    c13 = p_kp[:, [1, 3], 1] - p_kp[:, [5, 7], 1]
+    d_c = fu_kp * h3d / (F.relu(ch) * down_ratio + 1e-3)
+    d_02 = (fu_kp.unsqueeze(-1) * h3d.unsqueeze(-1) / (F.relu(c02) * down_ratio + 1e-3)).mean(1)
+    d_13 = (fu_kp.unsqueeze(-1) * h3d.unsqueeze(-1) / (F.relu(c13) * down_ratio + 1e-3)).mean(1)
+    p_kd = torch.stack([d_c, d_02, d_13], 1).clamp(0.1, 100)
+    p_kunc = pois[:, key2channel('corner_uncertainty')].clamp(*UNC_RANGE)
+    # soft_combine :241-248
+    unc = torch.cat((p_dunc.unsqueeze(-1), p_kunc), 1).exp()
+    depths = torch.cat((p_depth.unsqueeze(-1), p_kd), 1)
+    wts = 1 / unc
+    wts = wts / wts.sum(1, keepdim=True)
+    soft = (depths * wts).sum(1)
+    p_loc = unproject(pts, p_off, soft)
+    bin_cls = torch.softmax(p_ori[:, :8].view(-1, 4, 2), 2)[..., 1]        # decode_axes_orientation :245-295
+    bi = bin_cls.argmax(1)
+    offs = p_ori[:, 8:].view(-1, 4, 2)[torch.arange(p_ori.shape[0]), bi]
+    alpha = torch.atan2(offs[:, 0], offs[:, 1]) + torch.tensor([0, PI / 2, PI, -PI / 2])[bi]
+    roty = alpha + torch.atan2(p_loc[:, 0], p_loc[:, 2])
+    roty = torch.where(roty > PI, roty - 2 * PI, roty)
+    roty = torch.where(roty < -PI, roty + 2 * PI, roty)
+    p_corners = encode_box3d(roty, p_dims, p_loc)
+
+    w = LOSS_WEIGHTS
+    out, log = {}, {}
+    hl, npos = focal_loss(pred_cls, hm)
+    out['hm_loss'] = w['hm_loss'] * hl / torch.clamp(npos, 1)
+    l2d, iou = giou_loss(p_reg2d, t_reg2d)
+    out['bbox_loss'] = w['bbox_loss'] * l2d.mean()
+    log['2D_IoU'] = iou.mean().detach()
+    depth_mae = (p_depth - t_depth).abs() / t_depth
+    dl = w['depth_loss'] * (p_depth - t_depth).abs()
+    log['depth_loss'] = dl.detach().mean()
+    out['depth_loss'] = (dl * torch.exp(-p_dunc) + p_dunc * w['depth_loss']).mean()
+    ol = (p_off - t_off).abs().sum(1)
+    out['trunc_offset_loss'] = w['trunc_offset_loss'] * torch.log(1 + ol[trunc]).sum() / torch.clamp(trunc.sum(), min=1)
+    out['offset_loss'] = w['offset_loss'] * ol[~trunc].mean()
+    out['orien_loss'] = w['orien_loss'] * multibin_loss(p_ori, t_ori)
+    out['dims_loss'] = w['dims_loss'] * (p_dims - t_dims).abs().sum(1).mean()
+    out['corner_loss'] = w['corner_loss'] * (p_corners - t_corners).abs().sum(2).mean()
+    kl = w['keypoint_loss'] * (p_kp - t_kp).abs().sum(2) * t_kpm
+    out['keypoint_loss'] = kl.sum() / torch.clamp(t_kpm.sum(), min=1)
+    t_kd = t_depth.unsqueeze(-1).repeat(1, 3)
+    vl = w['keypoint_depth_loss'] * (p_kd[t_kdm] - t_kd[t_kdm]).abs()
+    il = w['keypoint_depth_loss'] * (p_kd[~t_kdm].detach() - t_kd[~t_kdm]).abs()
+    log['keypoint_depth_loss'] = vl.detach().mean()
+    vl = vl * torch.exp(-p_kunc[t_kdm]) + w['keypoint_depth_loss'] * p_kunc[t_kdm]
+    il = il * torch.exp(-p_kunc[~t_kdm])
+    out['keypoint_depth_loss'] = vl.sum() / torch.clamp(t_kdm.sum(), 1) + il.sum() / torch.clamp((~t_kdm).sum(), 1)
+    kmae = (p_kd - t_depth.unsqueeze(-1)).abs() / t_depth.unsqueeze(-1)
+    cmae = torch.cat((depth_mae.unsqueeze(1), kmae), 1)
+    out['weighted_avg_depth_loss'] = w['weighted_avg_depth_loss'] * (soft - t_depth).abs().mean()
+    log.update(depth_MAE=depth_mae.mean(), center_MAE=kmae[:, 0].mean(), **{'02_MAE': kmae[:, 1].mean(), '13_MAE': kmae[:, 2].mean()})
+    log['lower_MAE'] = cmae.min(1)[0].mean()
+    log['hard_MAE'] = cmae[torch.arange(cmae.shape[0]), unc.argmin(1)].mean()
+    log['soft_MAE'] = ((soft - t_depth).abs() / t_depth).mean()
+    log['mean_MAE'] = ((depths.mean(1) - t_depth).abs() / t_depth).mean()
+    return out, {k: v.detach() for k, v in log.items()}

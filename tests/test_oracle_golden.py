@@ -115,3 +115,32 @@ def test_oracle_ref_library_if_present():
                                             ctypes.c_void_p(mask[b].data_ptr()), 1, C, H, W, H, W, 3, 3, 1, 1, 1, 1, 1, 1, 1,
                                             ctypes.c_void_p(cols.data_ptr()))
         assert (ours[b] - cols).abs().max() < 1e-6
+
+
+def test_loss_oracle_matches_reference_loss_computation():
+    """oracle.loss_computation vs the UNMODIFIED reference Loss_Computation (oracle/make_golden_loss.py): the 11 loss
+    terms, the logged metrics and the autograd gradient of the summed loss w.r.t. both head outputs."""
+    import torch
+    from monoflex_b200 import synthetic as syn
+    gold = np.load(os.path.join(GOLDEN, "loss_4x96x320.npz"))
+    fields = syn.make_train_targets(4)
+    cls, reg = syn.make_train_predictions(4, fields)
+    cls.requires_grad_(True)
+    reg.requires_grad_(True)
+    loss, log = mo.loss_computation(cls, reg, fields, [syn.KITTI_P2] * 4)
+    assert set(loss) == set(mo.LOSS_NAMES)
+    for k, v in loss.items():
+        assert abs(v.item() - gold["loss_" + k]) <= 2e-6 * max(1.0, abs(gold["loss_" + k])), k
+    for k, v in log.items():
+        assert abs(v.item() - gold["log_" + k]) <= 2e-6 * max(1.0, abs(gold["log_" + k])), k
+    total = sum(loss.values())
+    total.backward()
+    centers = np.stack([f["target_centers"] for f in fields])
+    mask = np.stack([f["reg_mask"] for f in fields]).astype(bool)
+    g = reg.grad.numpy()
+    rows = np.stack([g[b, :, centers[b, i, 1], centers[b, i, 0]] for b in range(4) for i in range(mask.shape[1]) if mask[b, i]])
+    ref = gold["grad_reg_at_centers"]
+    assert np.abs(rows - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert abs(np.abs(g).sum() - gold["grad_reg_abs_sum"]) <= 1e-5 * gold["grad_reg_abs_sum"]
+    gc = cls.grad.numpy().reshape(-1)
+    assert np.abs(gc[::97] - gold["grad_cls_sample"]).max() <= 1e-5 * np.abs(gold["grad_cls_sample"]).max()
