@@ -115,6 +115,28 @@ int mf_focal_loss_forward(const float* pred, const float* target, long long n, f
 int mf_focal_loss_backward(const float* pred, const float* target, long long n, const float* scale, float* grad_pred,
                            void* stream);
 
+/* Loss_Computation.__call__ (model/head/detector_loss.py:267-493, prepare_predictions :116-265, Real_MultiBin_loss
+ * :495-517, IOULoss layers/iou_loss.py:12-49, decoders model/anno_encoder.py:88-295) for the runs/monoflex.yaml losses.
+ *   pred_cls [B,ncls,H,W] sigmoid-ed heat map, hm [B,ncls,H,W] label heat map, pred_reg [B,50,H,W]       (device, fp32)
+ *   obj [B*M, mf_loss_obj_cols()] packed per-object labels (device): 0 cls_id | 1-2 target_centers x,y | 3-6 2d_bboxes |
+ *       7 reg_mask | 8 trunc_mask | 9-11 dimensions | 12-14 locations | 15 rotys | 16-17 offset_3D | 18-25 orientations |
+ *       26-28 keypoints_depth_mask | 29-58 keypoints 10 x (x, y, visible)        (data/datasets/kitti.py:496-521)
+ *   img [B,8] (device): f_u f_v c_u c_v b_x b_y pad_x pad_y;  weights11 / dim_mean9: HOST arrays (INIT_LOSS_WEIGHT in
+ *       LOSS_NAMES order runs/monoflex.yaml:45-47, DIMENSION_MEAN config/defaults.py:206-208)
+ *   out48 (device): [0..10] the 11 losses in LOSS_NAMES order; [16..26] 2D_IoU, depth_loss(log), keypoint_depth_loss(log),
+ *       depth_MAE, center_MAE, 02_MAE, 13_MAE, lower_MAE, hard_MAE, soft_MAE, mean_MAE; [32..38] counts
+ *   ws64 (device): normalisers kept for the backward call.  No host synchronisation in either call.
+ * mf_loss_backward: grad_losses11 (device) = upstream gradient of each loss (ones for the trainer's plain sum,
+ * engine/trainer.py:109-110); writes grad_reg [B,50,H,W] (zero except at object centres) and grad_cls [B,ncls,H,W];
+ * either may be NULL. */
+int mf_loss_obj_cols(void);
+int mf_loss_forward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
+                    const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
+                    float* out48, float* ws64, void* stream);
+int mf_loss_backward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
+                     const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
+                     const float* ws64, const float* grad_losses11, float* grad_cls, float* grad_reg, void* stream);
+
 /* torch.optim.AdamW as configured by solver/__init__.py:10-37 (one param group per tensor, lr x BIAS_LR_FACTOR for
  * "bias" tensors, betas (0.9, 0.99), weight decay 1e-5) over ONE flat fp32 arena: every tensor starts at a multiple of
  * mf_adamw_chunk() elements and chunk_lr[n_chunks] (device) holds its group's lr (0 = padding / frozen). step is the

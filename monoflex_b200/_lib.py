@@ -32,6 +32,9 @@ SIGNATURES = {
     "mf_sigmoid_clamp": [_P, _LL, _P],
     "mf_focal_loss_forward": [_P, _P, _LL, _P, _P],
     "mf_focal_loss_backward": [_P, _P, _LL, _P, _P, _P],
+    "mf_loss_obj_cols": [],
+    "mf_loss_forward": [_P] * 7 + [_I] * 6 + [_P, _P, _P],
+    "mf_loss_backward": [_P] * 7 + [_I] * 6 + [_P, _P, _P, _P, _P],
     "mf_adamw_chunk": [],
     "mf_adamw_step": [_P, _P, _P, _P, _P, _LL, _F, _F, _F, _F, _LL, _F, _F, _P],
     "mf_nms_hm": [_P, _P, _I, _I, _I, _P],

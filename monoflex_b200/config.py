@@ -17,7 +17,14 @@ def default_cfg(width=1280, height=384, device="cuda"):
         ENABLE_EDGE_FUSION=True, EDGE_FUSION_KERNEL_SIZE=3, EDGE_FUSION_NORM='BN', EDGE_FUSION_RELU=False,
         DEPTH_MODE='inv_sigmoid', DEPTH_RANGE=[0.1, 100], OUTPUT_DEPTH='soft',
         DIMENSION_MEAN=((3.8840, 1.5261, 1.6286), (0.8423, 1.7607, 0.6602), (1.7635, 1.7372, 0.5968)),
-        DIMENSION_REG=['exp', True, False])
+        DIMENSION_REG=['exp', True, False],
+        # training losses (runs/monoflex.yaml:34-47 over config/defaults.py:137-197)
+        LOSS_TYPE=["Penalty_Reduced_FocalLoss", "L1", "giou", "L1"], HEATMAP_TYPE='centernet', LOSS_PENALTY_ALPHA=2, LOSS_BETA=4,
+        LOSS_NAMES=['hm_loss', 'bbox_loss', 'depth_loss', 'offset_loss', 'orien_loss', 'dims_loss', 'corner_loss',
+                    'keypoint_loss', 'keypoint_depth_loss', 'trunc_offset_loss', 'weighted_avg_depth_loss'],
+        INIT_LOSS_WEIGHT=[1, 1, 1, 0.5, 1, 1, 0.2, 1.0, 0.2, 0.1, 0.2], CORNER_LOSS_DEPTH='soft_combine',
+        TRUNCATION_OFFSET_LOSS='log', MODIFY_INVALID_KEYPOINT_DEPTH=True, UNCERTAINTY_RANGE=[-10, 10],
+        DIMENSION_WEIGHT=[1, 1, 1])
     cfg.INPUT = NS(WIDTH_TRAIN=width, HEIGHT_TRAIN=height, WIDTH_TEST=width, HEIGHT_TEST=height,
                    ORIENTATION='multi-bin', ORIENTATION_BIN_SIZE=4)
     cfg.DATASETS = NS(DETECT_CLASSES=("Car", "Pedestrian", "Cyclist"), TEST_SPLIT="test", MAX_OBJECTS=40)

@@ -18,6 +18,13 @@ int launch_edge_head_add(const __half* t, const float* w, const float* bias, int
                          cudaStream_t st);
 int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st);
 int launch_focal_loss(const float* pred, const float* tgt, long long n, float* out2, cudaStream_t st);
+#define MF_LOSS_OBJ_COLS 64   /* floats per (image, object slot) row of the packed label table (mf_loss.cu) */
+int launch_loss_forward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
+                        const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
+                        float* out48, float* ws64, cudaStream_t st);
+int launch_loss_backward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
+                         const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
+                         const float* ws64, const float* grad_losses11, float* grad_cls, float* grad_reg, cudaStream_t st);
 #define MF_ADAMW_CHUNK 512   /* arena granularity (elements) of the per-chunk lr table */
 int launch_focal_loss_backward(const float* pred, const float* tgt, long long n, const float* scale, float* grad,
                                cudaStream_t st);

@@ -114,3 +114,89 @@ def test_focal_loss_backward_matches_autograd():
     ref = pred.grad
     assert (grad.cpu() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
     assert grad.cpu()[tgt == -1].abs().sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ row R12: the 11-term loss
+def _loss_case(batch, seed=5):
+    from monoflex_b200 import synthetic as syn
+    fields = syn.make_train_targets(batch, seed=seed)
+    cls, reg = syn.make_train_predictions(batch, fields, seed=seed + 1)
+    return syn, fields, cls, reg
+
+
+def _run_cuda_loss(syn, fields, cls, reg):
+    from monoflex_b200.model.head.detector_loss import Loss_Computation
+    lc = Loss_Computation(default_cfg())
+    targets = [t.to("cuda") for t in syn.make_train_param_lists(fields)]
+    c, r = cls.clone().cuda().requires_grad_(True), reg.clone().cuda().requires_grad_(True)
+    loss_dict, log = lc({"cls": c, "reg": r}, targets)
+    return loss_dict, log, c, r
+
+
+@pytest.mark.parametrize("batch", [1, 4, 8])
+def test_loss_forward_matches_oracle(batch):
+    """11 losses + logged metrics of the fused kernel vs the CPU oracle (itself pinned against the unmodified reference,
+    tests/test_oracle_golden.py). batch 4 / 8 contain an image without objects (calibration-rank quirk), truncated
+    objects, objects without 2D box and invisible key points; batch 1 takes the reference's batch_size == 1 branch."""
+    syn, fields, cls, reg = _loss_case(batch)
+    if batch == 1:
+        fields = syn.make_train_targets(1, empty_image=-1)
+        cls, reg = syn.make_train_predictions(1, fields)
+    loss_dict, log, _, _ = _run_cuda_loss(syn, fields, cls, reg)
+    ref, ref_log = mo.loss_computation(cls, reg, fields, [syn.KITTI_P2] * batch)
+    assert list(loss_dict) == mo.LOSS_NAMES
+    for k in mo.LOSS_NAMES:
+        a, b = loss_dict[k].item(), ref[k].item()
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (k, a, b)
+    for k, v in ref_log.items():
+        assert abs(log[k] - v.item()) <= 1e-5 * max(1.0, abs(v.item())), (k, log[k], v.item())
+
+
+def test_loss_matches_reference_golden():
+    """straight against the fixture recorded from the unmodified reference (oracle/make_golden_loss.py)."""
+    import os
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "loss_4x96x320.npz"))
+    syn, fields, cls, reg = _loss_case(4)
+    loss_dict, log, c, r = _run_cuda_loss(syn, fields, cls, reg)
+    for k in mo.LOSS_NAMES:
+        assert abs(loss_dict[k].item() - gold["loss_" + k]) <= 1e-5 * max(1.0, abs(gold["loss_" + k])), k
+    total = sum(loss_dict.values())                                   # engine/trainer.py:110
+    assert abs(total.item() - gold["total"]) <= 1e-5 * abs(gold["total"])
+    total.backward()
+    centers = np.stack([f["target_centers"] for f in fields])
+    mask = np.stack([f["reg_mask"] for f in fields]).astype(bool)
+    g = r.grad.cpu().numpy()
+    rows = np.stack([g[b, :, centers[b, i, 1], centers[b, i, 0]] for b in range(4) for i in range(mask.shape[1]) if mask[b, i]])
+    ref = gold["grad_reg_at_centers"]
+    assert np.abs(rows - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert abs(np.abs(g).sum() - gold["grad_reg_abs_sum"]) <= 1e-4 * gold["grad_reg_abs_sum"]   # nothing outside the centres
+    gc = c.grad.cpu().numpy().reshape(-1)
+    assert np.abs(gc[::97] - gold["grad_cls_sample"]).max() <= 1e-5 * np.abs(gold["grad_cls_sample"]).max()
+
+
+def test_loss_backward_matches_oracle_autograd_weighted():
+    """dual-number backward with NON-uniform upstream gradients per loss term vs torch autograd through the oracle."""
+    syn, fields, cls, reg = _loss_case(8, seed=9)
+    wts = torch.tensor([0.3, 1.7, 0.9, 2.0, 0.5, 1.1, 3.0, 0.7, 1.3, 4.0, 0.2])
+    loss_dict, _, c, r = _run_cuda_loss(syn, fields, cls, reg)
+    sum(w * loss_dict[k] for w, k in zip(wts.cuda(), mo.LOSS_NAMES)).backward()
+    cr, rr = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref, _ = mo.loss_computation(cr, rr, fields, [syn.KITTI_P2] * 8)
+    sum(w * ref[k] for w, k in zip(wts, mo.LOSS_NAMES)).backward()
+    gr, gc = r.grad.cpu(), c.grad.cpu()
+    assert (gr - rr.grad).abs().max().item() <= 2e-5 * rr.grad.abs().max().item()
+    assert (gc - cr.grad).abs().max().item() <= 1e-5 * cr.grad.abs().max().item()
+    at_centre = torch.zeros_like(gr, dtype=torch.bool)                 # the gradient lives at the object centres only
+    for b, f in enumerate(fields):
+        for i in np.nonzero(f["reg_mask"])[0]:
+            at_centre[b, :, f["target_centers"][i, 1], f["target_centers"][i, 0]] = True
+    assert gr[~at_centre].abs().sum().item() == 0 and rr.grad[~at_centre].abs().sum().item() == 0
+
+
+def test_loss_config_guard():
+    from monoflex_b200.model.head.detector_loss import Loss_Computation
+    cfg = default_cfg()
+    cfg.MODEL.HEAD.CORNER_LOSS_DEPTH = 'direct'
+    with pytest.raises(NotImplementedError):
+        Loss_Computation(cfg)
