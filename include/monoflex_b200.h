@@ -143,6 +143,17 @@ int mf_loss_backward(const float* pred_cls, const float* hm, const float* pred_r
  * 1-based update count; grads are multiplied by grad_scale first (1/world_size after an NCCL SUM of the arena);
  * lr_scale is the scheduler's multiplier (solver/__init__.py:64-92). One launch, 28 B per parameter. */
 int mf_adamw_chunk(void);
+/* DDP gradient all-reduce (tools/plain_train_net.py:100-104) FUSED with the AdamW step for world > 1: one kernel over
+ * peer-mapped memory. param_ptrs / grad_ptrs: HOST arrays [world] of device addresses of every rank's parameter / gradient
+ * arena as mapped into THIS process (symmetric memory / CUDA IPC); mc_params / mc_grads: NVLS multicast addresses of the
+ * same arenas (both 0 = plain NVLink peer loads/stores). Rank r reduces the gradients of its 1/world shard of chunks
+ * (multimem.ld_reduce or a fixed-order peer sum), scales by 1/world, updates with ITS shard of exp_avg / exp_avg_sq, and
+ * writes the new parameters into all world arenas. The caller brackets the call with two cross-rank barriers (gradients
+ * complete everywhere before, parameters visible everywhere after). */
+int mf_adamw_step_p2p(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, int world, int rank,
+                      unsigned long long mc_params, unsigned long long mc_grads, float* exp_avg, float* exp_avg_sq,
+                      const float* chunk_lr, long long n_chunks, float beta1, float beta2, float eps, float weight_decay,
+                      long long step, float lr_scale, void* stream);
 int mf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* chunk_lr,
                   long long n_chunks, float beta1, float beta2, float eps, float weight_decay, long long step,
                   float grad_scale, float lr_scale, void* stream);

@@ -383,6 +383,13 @@ int mf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_
   return launch_adamw_arena(params, grads, exp_avg, exp_avg_sq, chunk_lr, n_chunks, beta1, beta2, eps, weight_decay, step,
                             grad_scale, lr_scale, MF_STREAM(stream));
 }
+int mf_adamw_step_p2p(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, int world, int rank,
+                      unsigned long long mc_params, unsigned long long mc_grads, float* exp_avg, float* exp_avg_sq,
+                      const float* chunk_lr, long long n_chunks, float beta1, float beta2, float eps, float weight_decay,
+                      long long step, float lr_scale, void* stream) {
+  return launch_adamw_p2p(param_ptrs, grad_ptrs, world, rank, mc_params, mc_grads, exp_avg, exp_avg_sq, chunk_lr, n_chunks,
+                          beta1, beta2, eps, weight_decay, step, lr_scale, MF_STREAM(stream));
+}
 int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream) {
   return launch_nms_hm(heat, out, planes, H, W, MF_STREAM(stream));
 }

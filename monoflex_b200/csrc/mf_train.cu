@@ -18,42 +18,149 @@ namespace mf {
 //   v   <- v * beta2 + (1 - beta2) * g * g          (torch: exp_avg_sq.mul_(beta2).addcmul_(g, g, value = 1 - beta2))
 //   p   <- p - (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
 // g is first multiplied by grad_scale (1 / world_size when the arena holds an NCCL SUM; 1 otherwise).
+struct AdamwConsts {
+  float beta1, beta2, eps, wd, bc1, rsqrt_bc2, grad_scale, lr_scale;
+};
+__device__ __forceinline__ void adamw_update4(float4& pp, const float4& gg, float4& mm, float4& vv, float lr,
+                                              const AdamwConsts& k) {
+  const float omb1 = 1.f - k.beta1, omb2 = 1.f - k.beta2;
+  const float decay = 1.f - lr * k.wd, step = lr / k.bc1;
+  float* pe = reinterpret_cast<float*>(&pp);
+  float* me = reinterpret_cast<float*>(&mm);
+  float* ve = reinterpret_cast<float*>(&vv);
+  const float* ge = reinterpret_cast<const float*>(&gg);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float gk = ge[e] * k.grad_scale;
+    float pk = pe[e] * decay;
+    const float mk = me[e] + (gk - me[e]) * omb1;
+    const float vk = ve[e] * k.beta2 + omb2 * gk * gk;
+    const float denom = sqrtf(vk) * k.rsqrt_bc2 + k.eps;
+    pk -= step * (mk / denom);
+    pe[e] = pk; me[e] = mk; ve[e] = vk;
+  }
+}
+
 __global__ void __launch_bounds__(256) adamw_arena_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const float* __restrict__ chunk_lr, long long n_chunks,
-                                                          float beta1, float beta2, float eps, float wd, float bc1,
-                                                          float rsqrt_bc2, float grad_scale, float lr_scale) {
+                                                          AdamwConsts k) {
   pdl_wait();
   constexpr int VEC_PER_CHUNK = MF_ADAMW_CHUNK / 4;
   const long long n_vec = n_chunks * VEC_PER_CHUNK;
-  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float lr = __ldg(chunk_lr + i / VEC_PER_CHUNK) * lr_scale;
+    const float lr = __ldg(chunk_lr + i / VEC_PER_CHUNK) * k.lr_scale;
     if (lr == 0.f) continue;                                   // padding-only chunk / frozen tensor
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    const float decay = 1.f - lr * wd, step = lr / bc1;
-    float* pe = reinterpret_cast<float*>(&pp);
-    float* me = reinterpret_cast<float*>(&mm);
-    float* ve = reinterpret_cast<float*>(&vv);
-    const float* ge = reinterpret_cast<const float*>(&gg);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gk = ge[k] * grad_scale;
-      float pk = pe[k] * decay;
-      const float mk = me[k] + (gk - me[k]) * omb1;
-      const float vk = ve[k] * beta2 + omb2 * gk * gk;
-      const float denom = sqrtf(vk) * rsqrt_bc2 + eps;
-      pk -= step * (mk / denom);
-      pe[k] = pk; me[k] = mk; ve[k] = vk;
-    }
+    adamw_update4(pp, gg, mm, vv, lr, k);
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
+}
+
+// ---------------------------------------------------------------- gradient exchange fused with the update (row R13, N > 1)
+// DDP's allreduce + optimizer.step (tools/plain_train_net.py:100-104, engine/trainer.py:116-121) as ONE kernel over peer
+// memory: every rank owns a contiguous 1/world shard of the arena's chunks. For its shard it
+//   1. reduces the gradient of all ranks - either `multimem.ld_reduce` on the NVLS multicast address (the NVSwitch adds
+//      the world copies in the fabric, one 16-byte request per float4) or a fixed-order sum of peer loads over NVLink;
+//   2. applies AdamW with ITS shard of the moments (the optimizer state is only ever touched by the owner: ZeRO-1);
+//   3. writes the new parameters into EVERY rank's parameter arena (`multimem.st` broadcast or peer stores).
+// Per rank and step that is 1/world of (world x 4 + 12) bytes per parameter read and world x 4 + 8 written, against NCCL
+// allreduce (2 x 4 x (world-1)/world over NVLink + 8 B HBM) followed by the 28 B/parameter update; the two system-scope
+// barriers around the kernel are the only other synchronisation. Each element is produced by exactly one rank with a
+// rank-independent summation order, so all replicas stay bit-identical.
+struct PeerPtrs {
+  float* p[MF_MAX_PEERS];
+  const float* g[MF_MAX_PEERS];
+};
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__global__ void __launch_bounds__(256) adamw_p2p_kernel(PeerPtrs peers, int world, int rank, float* mc_p, const float* mc_g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        const float* __restrict__ chunk_lr, long long chunk_lo,
+                                                        long long chunk_hi, AdamwConsts k) {
+  constexpr int VEC_PER_CHUNK = MF_ADAMW_CHUNK / 4;
+  const long long v_lo = chunk_lo * VEC_PER_CHUNK, v_hi = chunk_hi * VEC_PER_CHUNK;
+  for (long long i = v_lo + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < v_hi;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float lr = __ldg(chunk_lr + i / VEC_PER_CHUNK) * k.lr_scale;
+    if (lr == 0.f) continue;
+    float4 gg;
+    if (mc_g != nullptr) {
+      gg = multimem_ld_reduce_add(mc_g + 4 * i);
+    } else {
+      gg = __ldcg(reinterpret_cast<const float4*>(peers.g[0]) + i);
+      for (int r = 1; r < world; ++r) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(peers.g[r]) + i);
+        gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+      }
+    }
+    float4 pp = reinterpret_cast<const float4*>(peers.p[rank])[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_update4(pp, gg, mm, vv, lr, k);
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (mc_p != nullptr) {
+      multimem_st(mc_p + 4 * i, pp);
+    } else {
+      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.p[r])[i] = pp;
+    }
+  }
+}
+
+static AdamwConsts adamw_consts(float beta1, float beta2, float eps, float wd, long long step, float grad_scale,
+                                float lr_scale) {
+  // bias corrections in double like torch's Python scalars
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  AdamwConsts k;
+  k.beta1 = beta1; k.beta2 = beta2; k.eps = eps; k.wd = wd;
+  k.bc1 = static_cast<float>(bc1); k.rsqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  k.grad_scale = grad_scale; k.lr_scale = lr_scale;
+  return k;
+}
+
+int launch_adamw_p2p(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, int world, int rank,
+                     unsigned long long mc_params, unsigned long long mc_grads, float* m, float* v, const float* chunk_lr,
+                     long long n_chunks, float beta1, float beta2, float eps, float wd, long long step, float lr_scale,
+                     cudaStream_t st) {
+  if (world < 1 || world > MF_MAX_PEERS || rank < 0 || rank >= world) {
+    set_error("adamw_p2p: world %d (max %d) / rank %d", world, MF_MAX_PEERS, rank);
+    return -1;
+  }
+  if (step < 1) { set_error("adamw_p2p: step must be >= 1"); return -1; }
+  if ((mc_params == 0) != (mc_grads == 0)) { set_error("adamw_p2p: give both multicast addresses or neither"); return -1; }
+  PeerPtrs peers;
+  for (int r = 0; r < MF_MAX_PEERS; ++r) {
+    peers.p[r] = r < world ? reinterpret_cast<float*>(param_ptrs[r]) : nullptr;
+    peers.g[r] = r < world ? reinterpret_cast<const float*>(grad_ptrs[r]) : nullptr;
+  }
+  const long long base = n_chunks / world, extra = n_chunks % world;      // parallel.shard_range semantics
+  const long long lo = rank * base + (rank < extra ? rank : extra), hi = lo + base + (rank < extra ? 1 : 0);
+  if (hi <= lo) return 0;
+  const long long n_vec = (hi - lo) * (MF_ADAMW_CHUNK / 4);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = 148LL * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  const AdamwConsts k = adamw_consts(beta1, beta2, eps, wd, step, 1.f / static_cast<float>(world), lr_scale);
+  adamw_p2p_kernel<<<dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st>>>(
+      peers, world, rank, reinterpret_cast<float*>(mc_params), reinterpret_cast<const float*>(mc_grads), m, v, chunk_lr, lo,
+      hi, k);
+  return check_cuda(cudaGetLastError(), "adamw_p2p");
 }
 
 int launch_adamw_arena(float* p, const float* g, float* m, float* v, const float* chunk_lr, long long n_chunks,
@@ -61,16 +168,12 @@ int launch_adamw_arena(float* p, const float* g, float* m, float* v, const float
                        cudaStream_t st) {
   if (n_chunks <= 0) return 0;
   if (step < 1) { set_error("adamw: step must be >= 1 (1-based count of the update being applied)"); return -1; }
-  // bias corrections in double like torch's Python scalars
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
   const long long n_vec = n_chunks * (MF_ADAMW_CHUNK / 4);
   long long blocks = (n_vec + 255) / 256;
   const long long cap = 148LL * 8 * 4;                          // a few waves; grid-stride for the rest
   if (blocks > cap) blocks = cap;
   (void)launch_k(adamw_arena_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, p, g, m, v, chunk_lr,
-                 n_chunks, beta1, beta2, eps, wd, static_cast<float>(bc1), static_cast<float>(1.0 / sqrt(bc2)),
-                 grad_scale, lr_scale);
+                 n_chunks, adamw_consts(beta1, beta2, eps, wd, step, grad_scale, lr_scale));
   return check_cuda(cudaGetLastError(), "adamw_arena");
 }
 

@@ -39,7 +39,9 @@ class ParamArena:
     """Flat fp32 storage for a list of parameters: `.params`, `.grads` (and the AdamW moments) share one layout in which
     tensor i occupies [offset_i, offset_i + numel_i) and offset_i is a multiple of `chunk` elements."""
 
-    def __init__(self, tensors, chunk=ADAMW_CHUNK):
+    def __init__(self, tensors, chunk=ADAMW_CHUNK, alloc=None):
+        """alloc(numel, device) -> flat fp32 tensor; default torch.zeros (FusedAdamW passes a symmetric-memory allocator
+        when the fused NVLink gradient exchange is requested)."""
         tensors = list(tensors)
         if not tensors:
             raise ValueError("ParamArena: no parameters")
@@ -55,8 +57,10 @@ class ParamArena:
             off += -(-p.numel() // self.chunk) * self.chunk
         self.numel = off
         self.n_chunks = off // self.chunk
-        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        if alloc is None:
+            alloc = lambda n, d: torch.zeros(n, dtype=torch.float32, device=d)
+        self.params = alloc(off, dev)
+        self.grads = alloc(off, dev)
         with torch.no_grad():
             for p, o in zip(tensors, self.offsets):
                 n = p.numel()
@@ -108,7 +112,10 @@ class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW(model_params, lr, betas=(0.9, 0.99), weight_decay) (solver/__init__.py:36-37) with the update of
     ALL tensors in one kernel launch over a ParamArena."""
 
-    def __init__(self, params, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-5):
+    def __init__(self, params, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-5, symmetric_group=None):
+        """symmetric_group: a torch.distributed process group (NCCL, one rank per GPU of ONE NVLink domain). When given,
+        the parameter and gradient arenas are allocated in symmetric (peer-mapped) memory and `step_exchange()` replaces
+        `allreduce_grads(); step(grad_scale=1/world)` by the fused reduce-scatter + AdamW + all-gather kernel."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         tensors = [p for g in self.param_groups for p in g["params"]]
         if len({id(p) for p in tensors}) != len(tensors):
@@ -119,7 +126,20 @@ class FusedAdamW(torch.optim.Optimizer):
                                                               self.defaults["weight_decay"]):
                 raise NotImplementedError("FusedAdamW: betas / eps / weight_decay must be the same for every group "
                                           "(the reference only varies lr, solver/__init__.py:18-24)")
-        self.arena = ParamArena(tensors)
+        self._symm = None
+        alloc = None
+        if symmetric_group is not None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            def alloc(n, dev):
+                t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+                t.zero_()
+                return t
+        self.arena = ParamArena(tensors, alloc=alloc)
+        if symmetric_group is not None:
+            hp = symm_mem.rendezvous(self.arena.params, symmetric_group)
+            hg = symm_mem.rendezvous(self.arena.grads, symmetric_group)
+            self._symm = (hp, hg, symmetric_group)
         self.exp_avg = torch.zeros_like(self.arena.params)
         self.exp_avg_sq = torch.zeros_like(self.arena.params)
         self.step_count = 0
@@ -190,6 +210,40 @@ class FusedAdamW(torch.optim.Optimizer):
         for p in self.arena.tensors:            # cached kernel plans key on parameter versions (engine.fingerprint)
             torch.autograd.graph.increment_version(p)
         return None
+
+
+def _fused_exchange_step(self, use_multicast=True):
+    """DDP all-reduce + optimizer.step() as ONE kernel over NVLink peer memory (csrc/mf_train.cu adamw_p2p_kernel):
+    barrier -> every rank reduces, updates and re-broadcasts its 1/world shard -> barrier. Call after backward, on the
+    stream that produced the gradients. Needs FusedAdamW(..., symmetric_group=pg)."""
+    import ctypes
+    if self._symm is None:
+        raise RuntimeError("FusedAdamW.step_exchange: construct the optimiser with symmetric_group=<process group>")
+    from . import _lib
+    hp, hg, _ = self._symm
+    world, rank = hp.world_size, hp.rank
+    table = self._lr_table()
+    self.step_count += 1
+    b1, b2 = self.defaults["betas"]
+    pp = (ctypes.c_ulonglong * world)(*[int(x) for x in hp.buffer_ptrs])
+    gp = (ctypes.c_ulonglong * world)(*[int(x) for x in hg.buffer_ptrs])
+    mc_p = int(hp.multicast_ptr or 0) if use_multicast else 0     # 0 when the fabric / driver has no NVLS multicast
+    mc_g = int(hg.multicast_ptr or 0) if use_multicast else 0
+    if not (mc_p and mc_g):
+        mc_p = mc_g = 0
+    hg.barrier(channel=0)                       # every rank's backward has finished writing its gradient arena
+    _lib.call("mf_adamw_step_p2p", ctypes.addressof(pp), ctypes.addressof(gp), world, rank, mc_p, mc_g,
+              self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), table.data_ptr(), self.arena.n_chunks, b1, b2,
+              self.defaults["eps"], self.defaults["weight_decay"], self.step_count, 1.0,
+              torch.cuda.current_stream().cuda_stream)
+    hp.barrier(channel=1)                       # every shard of the new parameters has landed in every arena
+    self._step_t += 1
+    for p in self.arena.tensors:
+        torch.autograd.graph.increment_version(p)
+    return bool(mc_p)
+
+
+FusedAdamW.step_exchange = torch.no_grad()(_fused_exchange_step)
 
 
 def build_optimizer(model, cfg):

@@ -200,3 +200,20 @@ def test_loss_config_guard():
     cfg.MODEL.HEAD.CORNER_LOSS_DEPTH = 'direct'
     with pytest.raises(NotImplementedError):
         Loss_Computation(cfg)
+
+
+def test_fused_gradient_exchange_multi_gpu():
+    """world >= 2 only (skipped on a 1-GPU box): reduce-scatter + AdamW + all-gather in ONE peer-memory kernel is bit-identical
+    to NCCL all-reduce + the single-GPU kernel, for the plain NVLink and the NVLS multicast variants (tools/p2p_adamw_check.py)."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "p2p_adamw_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout

@@ -1,0 +1,87 @@
+"""N-GPU check + timing of the fused gradient exchange (row R13): NCCL all-reduce + one-launch AdamW (baseline) versus the
+single peer-memory kernel (reduce -> AdamW -> broadcast of each rank's shard), plain NVLink P2P and NVLS multicast variants.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_adamw_check.py
+Prints one JSON line on rank 0. Exit code != 0 on any mismatch."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from monoflex_b200 import parallel, solver, synthetic                 # noqa: E402
+
+
+def make_params(seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [s for _, s, kind in synthetic.dla34_param_shapes() if kind not in ("bn_m", "bn_v", "bn_n")]
+    return [torch.nn.Parameter((torch.randn(s, generator=g) * 0.05).cuda()) for s in shapes]
+
+
+def main():
+    rank, world, local = parallel.env_rank()
+    torch.cuda.set_device(local)
+    parallel.init("nccl", device=torch.device("cuda", local))
+    assert world > 1, "run under torchrun with >= 2 ranks"
+    steps, iters = 3, 20
+    res = {"world": world}
+    variants = [("p2p", False), ("multicast", True)]
+    base_p = make_params(0)
+    base = solver.FusedAdamW(base_p, lr=3e-4, weight_decay=1e-5)
+    fused = {}
+    for name, _ in variants:
+        fused[name] = solver.FusedAdamW(make_params(0), lr=3e-4, weight_decay=1e-5, symmetric_group=dist.group.WORLD)
+    n = sum(p.numel() for p in base_p)
+    res["params"] = n
+    ok = True
+    for it in range(steps):
+        g = torch.Generator(device="cuda").manual_seed(1000 * it + rank)
+        grads = torch.randn(base.arena.numel, generator=g, device="cuda") * 1e-2
+        base.arena.grads.copy_(grads)
+        w, _ = solver.allreduce_grads(base.arena)
+        base.step(grad_scale=1.0 / w)
+        for name, mc in variants:
+            opt = fused[name]
+            opt.arena.grads.copy_(grads)
+            used_mc = opt.step_exchange(use_multicast=mc)
+            res[name + "_used_multicast"] = bool(used_mc)
+            torch.cuda.synchronize()
+            d = (opt.arena.params - base.arena.params).abs().max().item()
+            res["%s_maxdiff_step%d" % (name, it)] = d
+            ok &= d <= 1e-7
+            # replicas must be bit-identical across ranks
+            cs = opt.arena.params.double().sum().reshape(1)
+            allcs = [torch.zeros_like(cs) for _ in range(world)]
+            dist.all_gather(allcs, cs)
+            ok &= all(torch.equal(allcs[0], c) for c in allcs)
+    # ---- timing: CUDA events, barrier + synchronize on both sides, max over ranks
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return parallel.max_over_ranks([e0.elapsed_time(e1) / iters], device="cuda")[0]
+
+    def f_base():
+        w, _ = solver.allreduce_grads(base.arena)
+        base.step(grad_scale=1.0 / w)
+    res["nccl_allreduce_plus_adamw_ms"] = timed(f_base)
+    for name, mc in variants:
+        res[name + "_fused_ms"] = timed(lambda: fused[name].step_exchange(use_multicast=mc))
+    res["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
