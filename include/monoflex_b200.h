@@ -72,10 +72,16 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
  * hid_col[i] >= 0, which are also stored to `hid` [B*H*W, hid_ld] at that column (edge fusion reads them).
  * w3_packed [nbranch*256, 9*Cin] fp16 (k = tap*Cin + c); w2_packed [nbranch*32, 256] fp16 (rows >= out_nch[i] zero);
  * bias2 [nbranch*32]; out_ptrs[i] = fp32 NCHW base pointer of branch i's first output channel (host array of device
- * pointers), out_ctot[i] = channel count of the tensor it points into, out_nch[i] <= 32 real channels. */
+ * pointers), out_ctot[i] = channel count of the tensor it points into, out_nch[i] <= 32 real channels.
+ * hid_mask (nullable) [B*H*W] bytes: when given only pixels with a non-zero flag are stored to `hid` (mf_edge_mask marks the
+ * border pixels the edge fusion gathers: ~830 of 30 720 per image, 245 MB less DRAM traffic per B = 8 forward). */
 int mf_head_fused(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w3_packed, const void* w2_packed,
                   const float* scale, const float* shift, const float* bias2, int nbranch, void* const* out_ptrs,
-                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld, void* stream);
+                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld,
+                  const unsigned char* hid_mask, void* stream);
+/* mask[b, y, x] = 1 for every pixel mf_edge_gather reads for edge_idx [B, K, 2] (x, y), 0 elsewhere */
+int mf_edge_mask(const long long* edge_idx, unsigned char* mask, int B, int K, int H, int W, int out_w, int out_h,
+                 void* stream);
 
 /* Fused DCNv2 (3x3, stride 1, pad 1, dilation 1, deformable_groups 1): bilinear gather of the modulated columns straight
  * into the MMA operand tile, contraction with the packed weights, affine (+bias, BN) and activation epilogue.

@@ -303,11 +303,16 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
 
 int mf_head_fused(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w3_packed, const void* w2_packed,
                   const float* scale, const float* shift, const float* bias2, int nbranch, void* const* out_ptrs,
-                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld, void* stream) {
+                  const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld,
+                  const unsigned char* hid_mask, void* stream) {
   return launch_head_fused(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(w3_packed),
                            static_cast<const __half*>(w2_packed), scale, shift, bias2, nbranch,
                            reinterpret_cast<float* const*>(out_ptrs), out_ctot, out_nch, hid_col, static_cast<__half*>(hid),
-                           hid_ld, MF_STREAM(stream));
+                           hid_ld, hid_mask, MF_STREAM(stream));
+}
+int mf_edge_mask(const long long* edge_idx, unsigned char* mask, int B, int K, int H, int W, int out_w, int out_h,
+                 void* stream) {
+  return launch_edge_mask(edge_idx, mask, B, K, H, W, out_w, out_h, MF_STREAM(stream));
 }
 
 int mf_dcn_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const float* offmask, int om_ld,

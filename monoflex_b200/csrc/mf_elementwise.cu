@@ -317,6 +317,35 @@ int launch_edge_gather(const __half* feat, int feat_ld, int ch_a, int ch_b, cons
   return check_cuda(cudaGetLastError(), "edge_gather");
 }
 
+// byte mask [B*H*W] of the pixels edge_gather_kernel reads (the up-to-4 bilinear corners of every border position, computed
+// with the same fp32 round trip), so that the fused head stores hidden activations for those pixels only.
+__global__ void edge_mask_kernel(const long long* __restrict__ edge_idx, unsigned char* __restrict__ mask, int B, int H,
+                                 int W, int K, int out_w, int out_h) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K;
+  const float ex = static_cast<float>(edge_idx[static_cast<long long>(i) * 2 + 0]);
+  const float ey = static_cast<float>(edge_idx[static_cast<long long>(i) * 2 + 1]);
+  const float gx = ex / static_cast<float>(out_w - 1) * 2.f - 1.f;
+  const float gy = ey / static_cast<float>(out_h - 1) * 2.f - 1.f;
+  const float ix = ((gx + 1.f) / 2.f) * static_cast<float>(W - 1);
+  const float iy = ((gy + 1.f) / 2.f) * static_cast<float>(H - 1);
+  const int x0 = static_cast<int>(floorf(ix)), y0 = static_cast<int>(floorf(iy));
+  unsigned char* mb = mask + static_cast<long long>(b) * H * W;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int yy = y0 + dy, xx = x0 + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) mb[yy * W + xx] = 1;
+    }
+}
+int launch_edge_mask(const long long* edge_idx, unsigned char* mask, int B, int K, int H, int W, int out_w, int out_h,
+                     cudaStream_t st) {
+  if (check_cuda(cudaMemsetAsync(mask, 0, static_cast<size_t>(B) * H * W, st), "edge_mask memset")) return -1;
+  (void)launch_k(edge_mask_kernel, dim3((B * K + 255) / 256), dim3(256), 0, st, edge_idx, mask, B, H, W, K, out_w, out_h);
+  return check_cuda(cudaGetLastError(), "edge_mask");
+}
+
 // final Conv1d(256 -> n_out, k=1) of one truncation branch + indexed add into an NCHW fp32 map
 // (detector_predictor.py:155-158). One warp per (b, e); lanes split the 256 input channels.
 __global__ void edge_head_add_kernel(const __half* __restrict__ t, const float* __restrict__ w,

@@ -37,7 +37,10 @@ struct HeadParams {
   int out_ctot[H_MAXBR];         // channels of the tensor it points into (batch stride = out_ctot*H*W)
   int out_nch[H_MAXBR];          // real output channels of the branch (<= 32)
   int hid_col[H_MAXBR];          // >= 0: hidden activations of this branch are stored at this column of `hid`
-};
+  __half* hid;                   // [M, hid_ld]
+  int hid_ld;
+  const unsigned char* hid_mask; // [M] or null. Non-null: only flagged pixels are stored (the ~830 border pixels per image
+};                               // the edge fusion gathers), by per-thread stores instead of a TMA store of every tile
 
 __global__ void __launch_bounds__(320, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -231,6 +234,12 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_before();
         mbar_arrive(&acc_empty[acc]);                          // accumulator is in registers: hand it back
         if (ti >= 1) mbar_wait(s2_done, (ti - 1) & 1);         // stage 2 of the previous tile no longer reads the staging
+        __half* hid_row = nullptr;                             // this thread's pixel is one the edge fusion will gather
+        if (p.hid_mask != nullptr && p.hid_col[br] >= 0) {
+          const int m = mt * HBM + row;
+          if (m < p.M && __ldg(p.hid_mask + m))
+            hid_row = p.hid + static_cast<long long>(m) * p.hid_ld + p.hid_col[br] + (nt & 1) * HBN;
+        }
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           const int ch = c2 * 2 + group;
@@ -241,13 +250,14 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[c2][i + 2 * e], v[c2][i + 2 * e + 1]);
             sts128(sub + sw128_off(row, (ch & 1) * 4 + (i >> 3)), *reinterpret_cast<uint4*>(o));
+            if (hid_row != nullptr) *reinterpret_cast<uint4*>(hid_row + ch * 32 + i) = *reinterpret_cast<uint4*>(o);
           }
         }
         fence_proxy_async();
         bar_sync_named(1, 256);
         if (et == 0) {
           store_pending = false;
-          if (p.hid_col[br] >= 0) {                            // hidden activations needed by the edge-fusion gather
+          if (p.hid_col[br] >= 0 && p.hid_mask == nullptr) {   // unmasked: store the whole tile of hidden activations
             const int col = p.hid_col[br] + (nt & 1) * HBN;
             tma_store_2d(&tmap_hid, o_u, col, mt * HBM);
             tma_store_2d(&tmap_hid, o_u + H_ASTAGE, col + 64, mt * HBM);
@@ -291,7 +301,7 @@ static void* driver_fn(const char* name) {
 int launch_head_fused(const __half* x, int x_ld, int B, int H, int W, int Cin, const __half* w3, const __half* w2,
                       const float* scale, const float* shift, const float* bias2, int nbranch, float* const* out,
                       const int* out_ctot, const int* out_nch, const int* hid_col, __half* hid, int hid_ld,
-                      cudaStream_t st) {
+                      const unsigned char* hid_mask, cudaStream_t st) {
   static PFN_encTiledH enc = reinterpret_cast<PFN_encTiledH>(driver_fn("cuTensorMapEncodeTiled"));
   static PFN_encIm2colH enc2 = reinterpret_cast<PFN_encIm2colH>(driver_fn("cuTensorMapEncodeIm2col"));
   if (!enc || !enc2) { set_error("head_fused: tensor-map driver entry points unavailable"); return -1; }
@@ -303,6 +313,7 @@ int launch_head_fused(const __half* x, int x_ld, int B, int H, int W, int Cin, c
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.M = B * H * W; p.nkb = 9 * Cin / 64; p.nbranch = nbranch;
   p.scale = scale; p.shift = shift; p.bias2 = bias2;
+  p.hid = hid; p.hid_ld = hid_ld; p.hid_mask = hid_mask;
   for (int i = 0; i < nbranch; ++i) {
     p.out[i] = out[i]; p.out_ctot[i] = out_ctot[i]; p.out_nch[i] = out_nch[i]; p.hid_col[i] = hid_col[i];
     if (out_nch[i] > 32) { set_error("head_fused: branch %d has %d > 32 output channels", i, out_nch[i]); return -1; }

@@ -43,7 +43,8 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
                      int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st);
 int launch_head_fused(const __half* x, int x_ld, int B, int H, int W, int Cin, const __half* w3, const __half* w2,
                       const float* scale, const float* shift, const float* bias2, int nbranch, float* const* out,
-                      const int* out_ctot, const int* out_nch, const int* hid_col, __half* hid, int hid_ld, cudaStream_t st);
+                      const int* out_ctot, const int* out_nch, const int* hid_col, __half* hid, int hid_ld,
+                      const unsigned char* hid_mask, cudaStream_t st);
 int launch_simt_gemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 
 }  // namespace mf

@@ -17,6 +17,8 @@ int launch_edge_head_add(const __half* t, const float* w, const float* bias, int
                          const long long* edge_len, float* out, int out_ctot, int out_ch0, int B, int K, int H, int W,
                          cudaStream_t st);
 int launch_sigmoid_clamp(float* x, long long n, cudaStream_t st);
+int launch_edge_mask(const long long* edge_idx, unsigned char* mask, int B, int K, int H, int W, int out_w, int out_h,
+                     cudaStream_t st);
 int launch_focal_loss(const float* pred, const float* tgt, long long n, float* out2, cudaStream_t st);
 #define MF_LOSS_OBJ_COLS 64   /* floats per (image, object slot) row of the packed label table (mf_loss.cu) */
 int launch_loss_forward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,

@@ -134,12 +134,21 @@ class _predictor(nn.Module):
             import ctypes
             arr_p = (ctypes.c_void_p * nb)(*out_ptrs)
             arr_ct, arr_nc, arr_hc = (ctypes.c_int * nb)(*out_ctot), (ctypes.c_int * nb)(*out_nch), (ctypes.c_int * nb)(*hid_col)
-            P.keep.extend([w2h, head_bias, hid_buf, arr_p, arr_ct, arr_nc, arr_hc, cls, reg])
+            P.edge_idx = torch.zeros(B, K_edge, 2, dtype=torch.long, device=dev)
+            hid_mask = None
+            if self.enable_edge_fusion and os.environ.get("MF_HID_FULL_STORE", "0") != "1":
+                # only the border pixels the edge fusion gathers need their hidden activations in HBM
+                hid_mask = torch.zeros(B * H * W, dtype=torch.uint8, device=dev)
+                ow_, oh_ = self.output_width, self.output_height
+                P.add("mf_edge_mask", lambda: (P.edge_idx.data_ptr(), hid_mask.data_ptr(), B, K_edge, H, W, ow_, oh_))
+            P.keep.extend([w2h, head_bias, hid_buf, hid_mask, arr_p, arr_ct, arr_nc, arr_hc, cls, reg])
             cin = feat.C
+            mask_ptr = hid_mask.data_ptr() if hid_mask is not None else None
             P.add("mf_head_fused", lambda: (
                 x.ptr(), x.ld, B, H, W, cin, w3.data_ptr(), w2h.data_ptr(), scale.data_ptr(), shift.data_ptr(), head_bias.data_ptr(),
                 nb, ctypes.cast(arr_p, ctypes.c_void_p), ctypes.cast(arr_ct, ctypes.c_void_p),
-                ctypes.cast(arr_nc, ctypes.c_void_p), ctypes.cast(arr_hc, ctypes.c_void_p), hid_buf.data_ptr(), hid_ld))
+                ctypes.cast(arr_nc, ctypes.c_void_p), ctypes.cast(arr_hc, ctypes.c_void_p), hid_buf.data_ptr(), hid_ld,
+                mask_ptr))
 
             class _Hid(object):
                 pass
@@ -164,7 +173,8 @@ class _predictor(nn.Module):
                                   self.num_reg)
                     ch += head.weight.shape[0]
             edge_cols = (0, (self.offset_index[0] + 1) * hc)
-        P.edge_idx = torch.zeros(B, K_edge, 2, dtype=torch.long, device=dev)
+        if not hasattr(P, "edge_idx"):
+            P.edge_idx = torch.zeros(B, K_edge, 2, dtype=torch.long, device=dev)
         P.edge_len = torch.zeros(B, dtype=torch.long, device=dev)
         if self.enable_edge_fusion:
             ea = P.act(B, 1, K_edge + 2, hc)
