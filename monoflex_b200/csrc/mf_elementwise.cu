@@ -150,33 +150,37 @@ __global__ void upsample_add_kernel(const __half* __restrict__ x, const float* _
   const long long t = pix / Wo;
   const int oy = static_cast<int>(t % Ho);
   const long long b = t / Ho;
-  float acc[8];
-  if (skip != nullptr) {
-    unpack8(__ldg(reinterpret_cast<const uint4*>(skip + pix * skip_ld + cv * 8)), acc);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  }
-  float up[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) up[e] = 0.f;
+  // issue the skip load and the (up to) four tap loads together, then do the arithmetic (latency-bound otherwise)
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const uint4 sk = skip != nullptr ? __ldg(reinterpret_cast<const uint4*>(skip + pix * skip_ld + cv * 8)) : zero4;
   const int iy_hi = (oy + pad) / f, ix_hi = (ox + pad) / f;
+  uint4 xin[2][2];
+  int tap[2][2];
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy) {
-    const int iy = iy_hi - dy, ky = oy + pad - iy * f;
-    if (iy < 0 || iy >= Hi || ky >= k) continue;
+  for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
-      const int ix = ix_hi - dx, kx = ox + pad - ix * f;
-      if (ix < 0 || ix >= Wi || kx >= k) continue;
+      const int iy = iy_hi - dy, ky = oy + pad - iy * f, ix = ix_hi - dx, kx = ox + pad - ix * f;
+      const bool ok = iy >= 0 && iy < Hi && ky < k && ix >= 0 && ix < Wi && kx < k;
+      tap[dy][dx] = ok ? ky * k + kx : -1;
+      xin[dy][dx] = ok ? __ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + iy) * Wi + ix) * x_ld + cv * 8)) : zero4;
+    }
+  float acc[8], up[8];
+  unpack8(sk, acc);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) up[e] = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      if (tap[dy][dx] < 0) continue;
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + iy) * Wi + ix) * x_ld + cv * 8)), v);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(ky * k + kx) * C + cv * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(ky * k + kx) * C + cv * 8 + 4));
+      unpack8(xin[dy][dx], v);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(tap[dy][dx]) * C + cv * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(tap[dy][dx]) * C + cv * 8 + 4));
       up[0] += v[0] * w0.x; up[1] += v[1] * w0.y; up[2] += v[2] * w0.z; up[3] += v[3] * w0.w;
       up[4] += v[4] * w1.x; up[5] += v[5] * w1.y; up[6] += v[6] * w1.z; up[7] += v[7] * w1.w;
     }
-  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] += up[e];
   *reinterpret_cast<uint4*>(y + pix * y_ld + cv * 8) = pack8(acc);
@@ -184,9 +188,9 @@ __global__ void upsample_add_kernel(const __half* __restrict__ x, const float* _
 // f == 2 (k = 4, pad 1) specialisation: one thread produces the 2x2 output block {2a+1, 2a+2} x {2b+1, 2b+2}, which depends
 // on exactly the four inputs (a..a+1, b..b+1): each input vector is loaded once instead of four times and every one of
 // the 16 kernel taps is used exactly once.
-__global__ void upsample2_add_kernel(const __half* __restrict__ x, const float* __restrict__ w,
-                                     const __half* __restrict__ skip, __half* __restrict__ y, int B, int Hi, int Wi, int C,
-                                     int x_ld, int skip_ld, int y_ld) {
+__global__ void __launch_bounds__(256, 3)
+upsample2_add_kernel(const __half* __restrict__ x, const float* __restrict__ w, const __half* __restrict__ skip,
+                     __half* __restrict__ y, int B, int Hi, int Wi, int C, int x_ld, int skip_ld, int y_ld) {
   pdl_wait();
   const int CV = C / 8, Ho = 2 * Hi, Wo = 2 * Wi;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -197,35 +201,35 @@ __global__ void upsample2_add_kernel(const __half* __restrict__ x, const float* 
   t /= (Wi + 1);
   const int a = static_cast<int>(t % (Hi + 1)) - 1;
   const long long b = t / (Hi + 1);
-  float in[2][2][8];
+  // all 8 global loads (4 inputs, 4 skip vectors) are issued before anything is consumed: the kernel is latency bound
+  // otherwise (measured 2 TB/s with the loads interleaved with the arithmetic at 2-3 resident blocks per SM)
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 xin[2][2], sk[2][2];
+  long long opix[2][2];
 #pragma unroll
   for (int iy = 0; iy < 2; ++iy)
 #pragma unroll
     for (int ix = 0; ix < 2; ++ix) {
       const int yy = a + iy, xx = bb + ix;
-      if (yy >= 0 && yy < Hi && xx >= 0 && xx < Wi) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + yy) * Wi + xx) * x_ld + cv * 8)), in[iy][ix]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) in[iy][ix][e] = 0.f;
-      }
+      xin[iy][ix] = (yy >= 0 && yy < Hi && xx >= 0 && xx < Wi)
+                        ? __ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + yy) * Wi + xx) * x_ld + cv * 8)) : zero4;
+      const int oy = 2 * a + 1 + iy, ox = 2 * bb + 1 + ix;             // (iy, ix) doubles as the output offset (dy, dx)
+      const bool ok = oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+      opix[iy][ix] = ok ? (b * Ho + oy) * Wo + ox : -1;
+      sk[iy][ix] = (ok && skip != nullptr) ? __ldg(reinterpret_cast<const uint4*>(skip + opix[iy][ix] * skip_ld + cv * 8)) : zero4;
     }
+  float in[2][2][8];
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) unpack8(xin[iy][ix], in[iy][ix]);
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
-    const int oy = 2 * a + 1 + dy;
-    if (oy < 0 || oy >= Ho) continue;
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
-      const int ox = 2 * bb + 1 + dx;
-      if (ox < 0 || ox >= Wo) continue;
-      const long long pix = (b * Ho + oy) * Wo + ox;
+      if (opix[dy][dx] < 0) continue;
       float acc[8], up[8];
-      if (skip != nullptr) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(skip + pix * skip_ld + cv * 8)), acc);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      }
+      unpack8(sk[dy][dx], acc);
 #pragma unroll
       for (int e = 0; e < 8; ++e) up[e] = 0.f;
       // same accumulation order as the generic kernel: input rows a+1 then a, columns b+1 then b
@@ -242,11 +246,10 @@ __global__ void upsample2_add_kernel(const __half* __restrict__ x, const float* 
         }
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += up[e];
-      *reinterpret_cast<uint4*>(y + pix * y_ld + cv * 8) = pack8(acc);
+      *reinterpret_cast<uint4*>(y + opix[dy][dx] * y_ld + cv * 8) = pack8(acc);
     }
   }
 }
-
 int launch_upsample_add(const __half* x, const float* w, const __half* skip, __half* y, int B, int Hi, int Wi, int C,
                         int f, int x_ld, int skip_ld, int y_ld, cudaStream_t st) {
   if (C % 8 || x_ld % 8 || y_ld % 8 || (skip && skip_ld % 8) || f < 1) { set_error("upsample_add: bad shape"); return -1; }
