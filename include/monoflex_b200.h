@@ -187,8 +187,12 @@ int mf_dcn_v2_forward(const float* x, const float* w, const float* bias, const f
                       int dw, int dg, void* workspace, size_t ws_bytes, void* stream);
 /* std::vector<at::Tensor>{dX,dOffset,dMask,dW,dB} dcn_v2_backward(input, weight, bias, offset, mask, grad_output, ...)
  * (src/dcn_v2.h:48-59, dcn_v2_cuda.cu:206-335): fp32 NCHW, caller-allocated gradients (they are overwritten, not
- * accumulated into). dX/dOffset/dMask use atomicAdd like the reference's col2im kernels (summation order not fixed).
- * Compatibility path for `_DCNv2.backward` (autograd / gradcheck); the fused training kernels are a later row. */
+ * accumulated into). dX uses atomicAdd like the reference's col2im kernel (summation order not fixed); dOffset, dMask, dW
+ * and dB are deterministic. workspace: caller-owned device scratch of at least mf_dcn_v2_backward_workspace(...) bytes
+ * (the grad-columns buffer [B, Cin*kh*kw, Ho*Wo] + the split-K partials of dW).
+ * Exact-fp32 operator path for `_DCNv2.backward` (autograd / gradcheck); smem-tiled CUDA-core GEMMs (mf_dcn_f32.cu). */
+size_t mf_dcn_v2_backward_workspace(int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
+                                    int dh, int dw, int dg);
 int mf_dcn_v2_backward(const float* x, const float* w, const float* bias, const float* offset, const float* mask,
                        const float* grad_y, float* grad_x, float* grad_offset, float* grad_mask, float* grad_w,
                        float* grad_bias, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,

@@ -44,6 +44,7 @@ SIGNATURES = {
                              _P, _P],
     "mf_dcn_v2_forward": [_P, _P, _P, _P, _P, _P] + [_I] * 14 + [_P, _SZ, _P],
     "mf_dcn_v2_backward": [_P] * 11 + [_I] * 14 + [_P, _SZ, _P],
+    "mf_dcn_v2_backward_workspace": [_I] * 14,
     "mf_dcn_v2_psroi_pooling_forward": [],
     "mf_dcn_v2_psroi_pooling_backward": [],
 }
@@ -62,7 +63,7 @@ def load():
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = args
-            fn.restype = _I
+            fn.restype = _SZ if name == "mf_dcn_v2_backward_workspace" else _I
         _lib = lib
         for i, name in enumerate(("MF_DCN_EXTRA_SMEM", "MF_CONV_EXTRA_SMEM", "MF_IGEMM_GEN1", "MF_NO_TMA_STORE", "MF_NO_TMA_IM2COL", "MF_TMA_SMALL_C", "MF_A_STATIONARY", "MF_DCN_WARPS_MODE", "MF_PDL", "MF_HEAD_CLUSTER")):     # experiments only
             if os.environ.get(name):

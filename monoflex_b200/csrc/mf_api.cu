@@ -46,201 +46,7 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, i
   return check_cuda(cudaGetLastError(), "pack_conv_weight");
 }
 
-// ---------------------------------------------------------------- boundary B: exact-fp32 DCNv2 forward, reference _ext layout
-// (NCHW fp32 in/out; src/dcn_v2.h:9-23, semantics of src/cuda/dcn_v2_im2col_cuda.cu:125-195 + dcn_v2_cuda.cu:126-163).
-// One thread per output element; no columns buffer. This is the operator-ABI compatibility path (testcuda.py KATs); the
-// detector's hot path uses the fused NHWC fp16 tensor-core kernel instead.
-__global__ void dcn_v2_forward_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                          const float* __restrict__ bias, const float* __restrict__ off,
-                                          const float* __restrict__ mask, float* __restrict__ y, int B, int Cin, int H,
-                                          int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
-                                          int dg, int Ho, int Wo) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Cout * Ho * Wo;
-  if (i >= total) return;
-  const int ox = static_cast<int>(i % Wo);
-  long long t = i / Wo;
-  const int oy = static_cast<int>(t % Ho);
-  t /= Ho;
-  const int o = static_cast<int>(t % Cout);
-  const int b = static_cast<int>(t / Cout);
-  const int taps = kh * kw, cpg = Cin / dg;
-  const long long HoWo = static_cast<long long>(Ho) * Wo, pix = static_cast<long long>(oy) * Wo + ox;
-  float acc = bias[o];
-  for (int g = 0; g < dg; ++g) {
-    const float* offp = off + (static_cast<long long>(b) * dg + g) * 2 * taps * HoWo;
-    const float* mp = mask + (static_cast<long long>(b) * dg + g) * taps * HoWo;
-    for (int tap = 0; tap < taps; ++tap) {
-      const int ki = tap / kw, kj = tap - ki * kw;
-      const float h_im = static_cast<float>(oy * sh - ph + ki * dh) + offp[(2 * tap) * HoWo + pix];
-      const float w_im = static_cast<float>(ox * sw - pw + kj * dw) + offp[(2 * tap + 1) * HoWo + pix];
-      if (!(h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(H) && w_im < static_cast<float>(W))) continue;
-      const float mk = mp[tap * HoWo + pix];
-      const float hlf = floorf(h_im), wlf = floorf(w_im);
-      const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
-      const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf), hi = hl + 1, wi = wl + 1;
-      const bool tp = hl >= 0, bt = hi <= H - 1, lf = wl >= 0, rt = wi <= W - 1;
-      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        const float* xp = x + (static_cast<long long>(b) * Cin + c) * H * W;
-        const float v1 = (tp && lf) ? xp[hl * W + wl] : 0.f;
-        const float v2 = (tp && rt) ? xp[hl * W + wi] : 0.f;
-        const float v3 = (bt && lf) ? xp[hi * W + wl] : 0.f;
-        const float v4 = (bt && rt) ? xp[hi * W + wi] : 0.f;
-        const float val = (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4) * mk;
-        acc += val * w[(static_cast<long long>(o) * Cin + c) * taps + tap];
-      }
-    }
-  }
-  y[i] = acc;
-}
-int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias, const float* off, const float* mask,
-                              float* y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
-                              int pw, int dh, int dw, int dg, cudaStream_t st) {
-  const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
-  const int Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
-  const long long n = static_cast<long long>(B) * Cout * Ho * Wo;
-  dcn_v2_forward_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, w, bias, off, mask, y, B, Cin, H, W,
-                                                                                   Cout, kh, kw, sh, sw, ph, pw, dh, dw,
-                                                                                   dg, Ho, Wo);
-  return check_cuda(cudaGetLastError(), "dcn_v2_forward_f32");
-}
-
-// ---------------------------------------------------------------- boundary B: DCNv2 backward, fp32, reference _ext layout
-// (src/dcn_v2.h:48-59; semantics of dcn_v2_cuda.cu:206-335 + im2col_cuda.cu:197-327). Three kernels, no columns buffer:
-//   data  : one thread per (b, c, tap, pixel): g = sum_o W[o,c,tap] dY[b,o,p]; scatters g*mask*bilinear-weights into dX
-//           (atomicAdd, like the reference's col2im) and accumulates dOffset / dMask over channels (atomicAdd).
-//   weight: one thread per (o, c, tap): sum over (b, p) of dY * (mask * bilinear sample)   (columns recomputed)
-//   bias  : one thread per o.
-// Compatibility path for `_DCNv2.backward` / gradcheck (testcuda.py:69-97); not the fused training kernels of row R5.
-struct DcnGeom {
-  int B, C, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
-};
-struct DcnSample {
-  float w1, w2, w3, w4;      // bilinear weights of the 4 corners (0 where the corner is outside)
-  float dh1, dh2, dh3, dh4;  // d(sample)/d(h) coefficients of the 4 corner values
-  float dw1, dw2, dw3, dw4;
-  int i1, i2, i3, i4;        // corner indices (clamped), valid only where the weight is non-zero
-  bool inside;
-};
-__device__ __forceinline__ DcnSample dcn_sample(const DcnGeom& g, float h_im, float w_im) {
-  DcnSample s;
-  s.inside = h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(g.H) && w_im < static_cast<float>(g.W);
-  s.w1 = s.w2 = s.w3 = s.w4 = s.dh1 = s.dh2 = s.dh3 = s.dh4 = s.dw1 = s.dw2 = s.dw3 = s.dw4 = 0.f;
-  s.i1 = s.i2 = s.i3 = s.i4 = 0;
-  if (!s.inside) return s;
-  const float hlf = floorf(h_im), wlf = floorf(w_im);
-  const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
-  const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf), hi = hl + 1, wi = wl + 1;
-  const bool tp = hl >= 0, bt = hi <= g.H - 1, lf = wl >= 0, rt = wi <= g.W - 1;
-  const int hlc = max(hl, 0), hic = min(hi, g.H - 1), wlc = max(wl, 0), wic = min(wi, g.W - 1);
-  s.i1 = hlc * g.W + wlc; s.i2 = hlc * g.W + wic; s.i3 = hic * g.W + wlc; s.i4 = hic * g.W + wic;
-  if (tp && lf) { s.w1 = hh * hw; s.dh1 = -hw; s.dw1 = -hh; }
-  if (tp && rt) { s.w2 = hh * lw; s.dh2 = -lw; s.dw2 = hh; }
-  if (bt && lf) { s.w3 = lh * hw; s.dh3 = hw; s.dw3 = -lh; }
-  if (bt && rt) { s.w4 = lh * lw; s.dh4 = lw; s.dw4 = lh; }
-  return s;
-}
-__global__ void dcn_bwd_data_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                    const float* __restrict__ off, const float* __restrict__ mask,
-                                    const float* __restrict__ dy, float* __restrict__ gx, float* __restrict__ goff,
-                                    float* __restrict__ gmask, const DcnGeom g) {
-  const int taps = g.kh * g.kw;
-  const long long HoWo = static_cast<long long>(g.Ho) * g.Wo;
-  const long long total = static_cast<long long>(g.B) * g.C * taps * HoWo;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long long pix = i % HoWo;
-  long long t = i / HoWo;
-  const int tap = static_cast<int>(t % taps);
-  t /= taps;
-  const int c = static_cast<int>(t % g.C);
-  const int b = static_cast<int>(t / g.C);
-  const int oy = static_cast<int>(pix / g.Wo), ox = static_cast<int>(pix % g.Wo);
-  const int grp = c / (g.C / g.dg);
-  const int ki = tap / g.kw, kj = tap - ki * g.kw;
-  const float* offp = off + (static_cast<long long>(b) * g.dg + grp) * 2 * taps * HoWo;
-  const float* mp = mask + (static_cast<long long>(b) * g.dg + grp) * taps * HoWo;
-  const float h_im = static_cast<float>(oy * g.sh - g.ph + ki * g.dh) + offp[(2 * tap) * HoWo + pix];
-  const float w_im = static_cast<float>(ox * g.sw - g.pw + kj * g.dw) + offp[(2 * tap + 1) * HoWo + pix];
-  const float mk = mp[tap * HoWo + pix];
-  float gcol = 0.f;     // gradient of the (c, tap, pix) column entry
-  for (int o = 0; o < g.Co; ++o)
-    gcol += w[(static_cast<long long>(o) * g.C + c) * taps + tap] * dy[(static_cast<long long>(b) * g.Co + o) * HoWo + pix];
-  const DcnSample s = dcn_sample(g, h_im, w_im);
-  if (!s.inside) return;
-  const float* xp = x + (static_cast<long long>(b) * g.C + c) * g.H * g.W;
-  float* gxp = gx + (static_cast<long long>(b) * g.C + c) * g.H * g.W;
-  const float v1 = xp[s.i1], v2 = xp[s.i2], v3 = xp[s.i3], v4 = xp[s.i4];
-  const float gm = gcol * mk;
-  if (s.w1 != 0.f) atomicAdd(gxp + s.i1, gm * s.w1);
-  if (s.w2 != 0.f) atomicAdd(gxp + s.i2, gm * s.w2);
-  if (s.w3 != 0.f) atomicAdd(gxp + s.i3, gm * s.w3);
-  if (s.w4 != 0.f) atomicAdd(gxp + s.i4, gm * s.w4);
-  const float val = s.w1 * v1 + s.w2 * v2 + s.w3 * v3 + s.w4 * v4;
-  const float dvh = s.dh1 * v1 + s.dh2 * v2 + s.dh3 * v3 + s.dh4 * v4;
-  const float dvw = s.dw1 * v1 + s.dw2 * v2 + s.dw3 * v3 + s.dw4 * v4;
-  float* gop = goff + (static_cast<long long>(b) * g.dg + grp) * 2 * taps * HoWo;
-  float* gmp = gmask + (static_cast<long long>(b) * g.dg + grp) * taps * HoWo;
-  atomicAdd(gop + (2 * tap) * HoWo + pix, gm * dvh);
-  atomicAdd(gop + (2 * tap + 1) * HoWo + pix, gm * dvw);
-  atomicAdd(gmp + tap * HoWo + pix, gcol * val);
-}
-__global__ void dcn_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ off,
-                                      const float* __restrict__ mask, const float* __restrict__ dy,
-                                      float* __restrict__ gw, const DcnGeom g) {
-  const int taps = g.kh * g.kw;
-  const long long total = static_cast<long long>(g.Co) * g.C * taps;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int tap = static_cast<int>(i % taps);
-  const int c = static_cast<int>((i / taps) % g.C);
-  const int o = static_cast<int>(i / (static_cast<long long>(taps) * g.C));
-  const int grp = c / (g.C / g.dg);
-  const int ki = tap / g.kw, kj = tap - ki * g.kw;
-  const long long HoWo = static_cast<long long>(g.Ho) * g.Wo;
-  float acc = 0.f;
-  for (int b = 0; b < g.B; ++b) {
-    const float* offp = off + (static_cast<long long>(b) * g.dg + grp) * 2 * taps * HoWo;
-    const float* mp = mask + (static_cast<long long>(b) * g.dg + grp) * taps * HoWo;
-    const float* xp = x + (static_cast<long long>(b) * g.C + c) * g.H * g.W;
-    const float* dyp = dy + (static_cast<long long>(b) * g.Co + o) * HoWo;
-    for (int oy = 0; oy < g.Ho; ++oy)
-      for (int ox = 0; ox < g.Wo; ++ox) {
-        const long long pix = static_cast<long long>(oy) * g.Wo + ox;
-        const float h_im = static_cast<float>(oy * g.sh - g.ph + ki * g.dh) + offp[(2 * tap) * HoWo + pix];
-        const float w_im = static_cast<float>(ox * g.sw - g.pw + kj * g.dw) + offp[(2 * tap + 1) * HoWo + pix];
-        const DcnSample s = dcn_sample(g, h_im, w_im);
-        if (!s.inside) continue;
-        const float val = s.w1 * xp[s.i1] + s.w2 * xp[s.i2] + s.w3 * xp[s.i3] + s.w4 * xp[s.i4];
-        acc += dyp[pix] * val * mp[tap * HoWo + pix];
-      }
-  }
-  gw[i] = acc;
-}
-__global__ void dcn_bwd_bias_kernel(const float* __restrict__ dy, float* __restrict__ gb, int B, int Co, long long HoWo) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= Co) return;
-  float acc = 0.f;
-  for (int b = 0; b < B; ++b)
-    for (long long p = 0; p < HoWo; ++p) acc += dy[(static_cast<long long>(b) * Co + o) * HoWo + p];
-  gb[o] = acc;
-}
-int launch_dcn_v2_backward_f32(const float* x, const float* w, const float* off, const float* mask, const float* dy,
-                               float* gx, float* goff, float* gmask, float* gw, float* gb, const DcnGeom& g,
-                               cudaStream_t st) {
-  const int taps = g.kh * g.kw;
-  const long long HoWo = static_cast<long long>(g.Ho) * g.Wo;
-  if (check_cuda(cudaMemsetAsync(gx, 0, sizeof(float) * g.B * g.C * g.H * g.W, st), "memset gx")) return -1;
-  if (check_cuda(cudaMemsetAsync(goff, 0, sizeof(float) * g.B * g.dg * 2 * taps * HoWo, st), "memset goff")) return -1;
-  if (check_cuda(cudaMemsetAsync(gmask, 0, sizeof(float) * g.B * g.dg * taps * HoWo, st), "memset gmask")) return -1;
-  const long long n1 = static_cast<long long>(g.B) * g.C * taps * HoWo;
-  dcn_bwd_data_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(x, w, off, mask, dy, gx, goff, gmask, g);
-  const long long n2 = static_cast<long long>(g.Co) * g.C * taps;
-  dcn_bwd_weight_kernel<<<static_cast<unsigned>((n2 + 127) / 128), 128, 0, st>>>(x, off, mask, dy, gw, g);
-  dcn_bwd_bias_kernel<<<(g.Co + 127) / 128, 128, 0, st>>>(dy, gb, g.B, g.Co, HoWo);
-  return check_cuda(cudaGetLastError(), "dcn_v2_backward_f32");
-}
+// boundary B (exact-fp32 `_ext.dcn_v2_forward/backward` on NCHW tensors): kernels and launchers live in mf_dcn_f32.cu
 
 static int run_gemm(const IgemmParams& p, const void* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
   if (g_conv_impl == 1) return launch_simt_gemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
@@ -410,23 +216,20 @@ int mf_dcn_v2_forward(const float* x, const float* w, const float* bias, const f
                       int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
                       int dw, int dg, void* workspace, size_t ws_bytes, void* stream) {
   (void)workspace; (void)ws_bytes;
-  if (dg < 1 || Cin % dg != 0) { set_error("mf_dcn_v2_forward: channels %d not divisible by deformable_group %d", Cin, dg); return -1; }
   return launch_dcn_v2_forward_f32(x, w, bias, offset, mask, y, B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg,
                                    MF_STREAM(stream));
+}
+size_t mf_dcn_v2_backward_workspace(int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
+                                    int dh, int dw, int dg) {
+  return dcn_v2_backward_f32_workspace(B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg);
 }
 int mf_dcn_v2_backward(const float* x, const float* w, const float* bias, const float* offset, const float* mask,
                        const float* grad_y, float* grad_x, float* grad_offset, float* grad_mask, float* grad_w,
                        float* grad_bias, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
                        int pw, int dh, int dw, int dg, void* workspace, size_t ws_bytes, void* stream) {
-  (void)bias; (void)workspace; (void)ws_bytes;
-  if (dg < 1 || Cin % dg != 0) { set_error("mf_dcn_v2_backward: channels %d not divisible by deformable_group %d", Cin, dg); return -1; }
-  DcnGeom g;
-  g.B = B; g.C = Cin; g.H = H; g.W = W; g.Co = Cout; g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.ph = ph; g.pw = pw;
-  g.dh = dh; g.dw = dw; g.dg = dg;
-  g.Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
-  g.Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
-  return launch_dcn_v2_backward_f32(x, w, offset, mask, grad_y, grad_x, grad_offset, grad_mask, grad_w, grad_bias, g,
-                                    MF_STREAM(stream));
+  (void)bias;
+  return launch_dcn_v2_backward_f32(x, w, offset, mask, grad_y, grad_x, grad_offset, grad_mask, grad_w, grad_bias, B, Cin, H,
+                                    W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, workspace, ws_bytes, MF_STREAM(stream));
 }
 int mf_dcn_v2_psroi_pooling_forward(void) {
   set_error("dcn_v2_psroi_pooling_forward: not built (dead code for MonoFlex, SURVEY 2.2 K6)");

@@ -48,4 +48,10 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, i
 int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                               float* y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
                               int pw, int dh, int dw, int dg, cudaStream_t st);
+size_t dcn_v2_backward_f32_workspace(int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
+                                     int dh, int dw, int dg);
+int launch_dcn_v2_backward_f32(const float* x, const float* w, const float* off, const float* mask, const float* dy,
+                               float* gx, float* goff, float* gmask, float* gw, float* gb, int B, int Cin, int H, int W,
+                               int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int dg,
+                               void* workspace, size_t ws_bytes, cudaStream_t st);
 }  // namespace mf

@@ -7,7 +7,7 @@ Inputs must be fp32 CUDA tensors; like the reference (dcn_v2_cuda.cu:60-84) anyt
 Outputs are freshly allocated tensors owned by the caller; the kernel runs asynchronously on the current stream."""
 import torch
 
-from ...._lib import call, stream
+from ...._lib import call, load, stream
 
 
 def _check(name, t):
@@ -49,9 +49,14 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
     Co = w.shape[0]
     gx, gw, gb = torch.empty_like(x), torch.empty_like(w), torch.empty_like(b)
     go, gm = torch.empty_like(off), torch.empty_like(m)
+    geom = (B, C, H, W, Co, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group)
+    ws_bytes = load().mf_dcn_v2_backward_workspace(*geom)
+    if ws_bytes == 0:
+        raise RuntimeError("dcn_v2_backward: " + load().mf_last_error().decode())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)          # grad-columns buffer + split-K partials of dW
     call("mf_dcn_v2_backward", x.data_ptr(), w.data_ptr(), b.data_ptr(), off.data_ptr(), m.data_ptr(), gy.data_ptr(),
          gx.data_ptr(), go.data_ptr(), gm.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, C, H, W, Co, kernel_h, kernel_w,
-         stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, None, 0, stream())
+         stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, deformable_group, ws.data_ptr(), ws_bytes, stream())
     return gx, go, gm, gw, gb
 
 

@@ -237,6 +237,43 @@ def test_ext_dcn_v2_backward_vs_oracle_autograd_and_gradcheck():
     print("fp32 gradcheck (reference recipe, informational):", ok)
 
 
+@pytest.mark.parametrize("geom", [
+    # B, C, Co, H, W, kh, kw, sh, sw, ph, pw, dh, dw, dg
+    (2, 8, 6, 9, 11, 3, 3, 2, 2, 1, 1, 1, 1, 2),          # stride 2, two deformable groups
+    (1, 6, 70, 8, 10, 3, 5, 1, 1, 1, 2, 1, 1, 1),         # rectangular kernel, Co > one 64-row tile
+    (2, 20, 5, 10, 12, 3, 3, 1, 2, 2, 2, 2, 2, 4),        # dilation 2, mixed strides, 4 groups, C > one 16-deep k step
+    (1, 3, 4, 70, 67, 1, 1, 1, 1, 0, 0, 1, 1, 1),         # 1x1 kernel, > 64 pixels per row tile with a ragged tail
+])
+def test_ext_dcn_v2_general_geometry(geom):
+    """Boundary B honours every argument of src/dcn_v2.h:9-23 (kernel, stride, pad, dilation, deformable groups), forward
+    and all five gradients. Checker: torchvision.ops.deform_conv2d on CPU (an independent implementation of the same
+    DCNv2 definition; the 3x3/s1/p1 case is pinned against the reference's own C loops above)."""
+    from torchvision.ops import deform_conv2d
+    from monoflex_b200.model.backbone.DCNv2 import _ext
+    B, C, Co, H, W, kh, kw, sh, sw, ph, pw, dh, dw, dg = geom
+    gen = np.random.Generator(np.random.PCG64(hash(geom) % 1000))
+    Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    x = t(gen.standard_normal((B, C, H, W)))
+    off = t(gen.standard_normal((B, 2 * dg * kh * kw, Ho, Wo)) * 1.5)
+    mask = t(gen.uniform(0.1, 0.9, (B, dg * kh * kw, Ho, Wo)))
+    w = t(gen.standard_normal((Co, C, kh, kw)) * 0.3)
+    bias = t(gen.standard_normal(Co))
+    gy = t(gen.standard_normal((B, Co, Ho, Wo)))
+    leaves = [v.clone().requires_grad_(True) for v in (x, w, bias, off, mask)]
+    ref = deform_conv2d(leaves[0], leaves[3], leaves[1], leaves[2], stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw),
+                        mask=leaves[4])
+    ref.backward(gy)
+    args = (kh, kw, sh, sw, ph, pw, dh, dw, dg)
+    y = _ext.dcn_v2_forward(x.cuda(), w.cuda(), bias.cuda(), off.cuda(), mask.cuda(), *args)
+    assert y.shape == ref.shape and rel_err(y.cpu(), ref.detach()) < 1e-5
+    gx, go, gm, gw, gb = _ext.dcn_v2_backward(x.cuda(), w.cuda(), bias.cuda(), off.cuda(), mask.cuda(), gy.cuda(), *args)
+    for name, got, want in (("dX", gx, leaves[0].grad), ("dW", gw, leaves[1].grad), ("dB", gb, leaves[2].grad),
+                            ("dOff", go, leaves[3].grad), ("dMask", gm, leaves[4].grad)):
+        assert rel_err(got.cpu(), want) < 1e-4, name
+
+
 def test_maxpool_and_upsample_add():
     gen = np.random.Generator(np.random.PCG64(7))
     x = h16(torch.from_numpy(gen.standard_normal((2, 64, 12, 20)).astype(np.float32)))
