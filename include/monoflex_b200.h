@@ -122,6 +122,10 @@ int mf_focal_loss_forward(const float* pred, const float* target, long long n, f
 int mf_focal_loss_backward(const float* pred, const float* target, long long n, const float* scale, float* grad_pred,
                            void* stream);
 
+/* diagnostics: D[128,128] = A^T B with A [64,128] and B [64,128] fp16 row-major (reduction index = rows), computed with
+ * MN-major tcgen05 operand descriptors - the operand form the weight-gradient GEMM of the training path needs */
+int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream);
+
 /* Loss_Computation.__call__ (model/head/detector_loss.py:267-493, prepare_predictions :116-265, Real_MultiBin_loss
  * :495-517, IOULoss layers/iou_loss.py:12-49, decoders model/anno_encoder.py:88-295) for the runs/monoflex.yaml losses.
  *   pred_cls [B,ncls,H,W] sigmoid-ed heat map, hm [B,ncls,H,W] label heat map, pred_reg [B,50,H,W]       (device, fp32)

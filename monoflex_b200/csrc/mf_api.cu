@@ -174,6 +174,9 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
                            void* stream) {
   return launch_focal_loss_backward(pred, target, n, scale, grad_pred, MF_STREAM(stream));
 }
+int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream) {
+  return launch_mn_major_selftest(static_cast<const __half*>(a_km), static_cast<const __half*>(b_kn), d_mn, MF_STREAM(stream));
+}
 int mf_loss_obj_cols(void) { return MF_LOSS_OBJ_COLS; }
 int mf_loss_forward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
                     const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,

@@ -27,6 +27,7 @@ int launch_loss_forward(const float* pred_cls, const float* hm, const float* pre
 int launch_loss_backward(const float* pred_cls, const float* hm, const float* pred_reg, const float* obj, const float* img,
                          const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
                          const float* ws64, const float* grad_losses11, float* grad_cls, float* grad_reg, cudaStream_t st);
+int launch_mn_major_selftest(const __half* a_km, const __half* b_kn, float* d_mn, cudaStream_t st);
 #define MF_MAX_PEERS 16
 int launch_adamw_p2p(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, int world, int rank,
                      unsigned long long mc_params, unsigned long long mc_grads, float* m, float* v, const float* chunk_lr,

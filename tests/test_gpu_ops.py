@@ -398,3 +398,18 @@ def test_focal_loss_kernel():
     call("mf_focal_loss_forward", p.data_ptr(), t.data_ptr(), p.numel(), out.data_ptr(), stream())
     loss, npos = mo.focal_loss(pred, tgt)
     assert abs(out[0].item() - loss.item()) < 1e-4 * abs(loss.item()) and out[1].item() == npos.item()
+
+
+def test_tcgen05_mn_major_operands():
+    """MN-major (transposed) tcgen05 operand descriptors (csrc/mf_selftest.cu): D = A^T B with the reduction index as the
+    memory row index of both operands - the form the weight-gradient GEMM of the training rows will use. Exact in fp32
+    accumulation order up to re-association."""
+    from monoflex_b200._lib import call, stream
+    gen = np.random.Generator(np.random.PCG64(77))
+    a = torch.from_numpy(gen.standard_normal((64, 128)).astype(np.float32)).half()
+    b = torch.from_numpy(gen.standard_normal((64, 128)).astype(np.float32)).half()
+    d = torch.zeros(128, 128, dtype=torch.float32, device="cuda")
+    ac, bc = a.cuda(), b.cuda()
+    call("mf_selftest_mn_major", ac.data_ptr(), bc.data_ptr(), d.data_ptr(), stream())
+    ref = a.float().t() @ b.float()
+    assert rel_err(d.cpu(), ref) < 1e-5
