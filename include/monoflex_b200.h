@@ -122,6 +122,13 @@ int mf_focal_loss_forward(const float* pred, const float* target, long long n, f
 int mf_focal_loss_backward(const float* pred, const float* target, long long n, const float* scale, float* grad_pred,
                            void* stream);
 
+/* Convolution weight gradient (backward of `nn.Conv2d` in BasicBlock / Root / IDA nodes, model/backbone/dla_dcn.py:69-203):
+ *   dw[co, ci, ky, kx] = sum_{b, oy, ox} dy[b, oy, ox, co] * x[b, oy*stride - pad + ky, ox*stride - pad + kx, ci]
+ * x [B*H*W, x_ld], dy [B*Ho*Wo, dy_ld] fp16 NHWC rows; dw fp32 OIHW, overwritten. Cin, Cout multiples of 64, square kernel.
+ * tcgen05 GEMM with MN-major operands fed by im2col / tiled TMA, split-K with fp32 atomics (summation order not fixed). */
+int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
+                             int stride, int pad, float* dw, void* stream);
+
 /* diagnostics: D[128,128] = A^T B with A [64,128] and B [64,128] fp16 row-major (reduction index = rows), computed with
  * MN-major tcgen05 operand descriptors - the operand form the weight-gradient GEMM of the training path needs */
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream);

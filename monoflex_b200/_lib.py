@@ -33,6 +33,7 @@ SIGNATURES = {
     "mf_sigmoid_clamp": [_P, _LL, _P],
     "mf_focal_loss_forward": [_P, _P, _LL, _P, _P],
     "mf_focal_loss_backward": [_P, _P, _LL, _P, _P, _P],
+    "mf_conv2d_wgrad_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P],
     "mf_selftest_mn_major": [_P, _P, _P, _P],
     "mf_loss_obj_cols": [],
     "mf_loss_forward": [_P] * 7 + [_I] * 6 + [_P, _P, _P],

@@ -174,6 +174,11 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
                            void* stream) {
   return launch_focal_loss_backward(pred, target, n, scale, grad_pred, MF_STREAM(stream));
 }
+int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
+                             int stride, int pad, float* dw, void* stream) {
+  return launch_conv_wgrad(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(dy), dy_ld, Cout, k,
+                           stride, pad, dw, MF_STREAM(stream));
+}
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream) {
   return launch_mn_major_selftest(static_cast<const __half*>(a_km), static_cast<const __half*>(b_kn), d_mn, MF_STREAM(stream));
 }

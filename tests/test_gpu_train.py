@@ -217,3 +217,35 @@ def test_fused_gradient_exchange_multi_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"ok": true' in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ conv backward building blocks
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, k, stride, pad
+    (2, 12, 20, 64, 64, 3, 1, 1),        # two taps share an M tile; 9 taps -> a dummy half tile
+    (2, 14, 18, 128, 128, 3, 2, 1),      # stride 2, N = 128, ragged last pixel block
+    (1, 9, 23, 64, 256, 1, 1, 0),        # 1x1, two N tiles
+    (2, 10, 12, 192, 64, 3, 1, 1),       # odd number of 64-channel slots
+    (8, 96, 320, 64, 64, 3, 1, 1),       # full-size level-2 layer: long split-K reduction
+])
+def test_conv_wgrad_tensor_core(case):
+    """dW of a convolution from NHWC fp16 activations / output gradients (MN-major tcgen05 operands, split-K) vs
+    torch.nn.grad.conv2d_weight on the same fp16-representable operands in fp32 (CPU)."""
+    from monoflex_b200._lib import call, stream
+    B, H, W, Cin, Cout, k, s, pad = case
+    gen = np.random.Generator(np.random.PCG64(sum(case)))
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    x = torch.from_numpy(gen.standard_normal((B, Cin, H, W)).astype(np.float32)).half()
+    dy = torch.from_numpy((gen.standard_normal((B, Cout, Ho, Wo)) * 0.1).astype(np.float32)).half()
+    xr = x.permute(0, 2, 3, 1).reshape(-1, Cin).contiguous().cuda()
+    dyr = dy.permute(0, 2, 3, 1).reshape(-1, Cout).contiguous().cuda()
+    dw = torch.full((Cout, Cin, k, k), float("nan"), dtype=torch.float32, device="cuda")
+    call("mf_conv2d_wgrad_nhwc_f16", xr.data_ptr(), Cin, B, H, W, Cin, dyr.data_ptr(), Cout, Cout, k, s, pad, dw.data_ptr(),
+         stream())
+    if B * H * W > 100000:       # CPU reference of the big case in chunks of images (conv2d_weight is slow but exact enough)
+        ref = sum(torch.nn.grad.conv2d_weight(x[b:b + 1].float(), (Cout, Cin, k, k), dy[b:b + 1].float(), stride=s, padding=pad)
+                  for b in range(B))
+    else:
+        ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, k, k), dy.float(), stride=s, padding=pad)
+    err = (dw.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4, err
