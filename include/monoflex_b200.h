@@ -129,6 +129,23 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
 int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
                              int stride, int pad, float* dw, void* stream);
 
+/* Training-mode nn.BatchNorm2d(momentum 0.1) / InPlaceABN over NHWC fp16 rows (dla_dcn.py:76-79, detector_predictor.py:50,74;
+ * eval mode is folded into the conv epilogues instead). x = raw conv output [M, x_ld], C channels (multiple of 8).
+ * forward: batch mean / biased variance (deterministic two-level reduction), running-stat update like torch (unbiased
+ *   variance, skipped when running_mean is NULL), y = act(x * scale + shift [+ res]); act 0 none / 1 ReLU / 2 leaky 0.01;
+ *   abs_gamma = 1 uses |gamma| + eps (InPlaceABN). Outputs mean, rstd, scale, shift [C] are kept for the backward call.
+ * backward: g = dy * act'(y); dgamma = sum g * xhat, dbeta = sum g; dx = scale * (g - mean(g) - xhat * mean(g * xhat));
+ *   dres (nullable) receives g (gradient of the residual input).
+ * workspace: mf_bn_train_workspace(M, C) bytes of device scratch. */
+size_t mf_bn_train_workspace(long long M, int C);
+int mf_bn_train_forward(const void* x, int x_ld, long long M, int C, const float* gamma, const float* beta, float eps,
+                        float momentum, int abs_gamma, float* running_mean, float* running_var, const void* res, int res_ld,
+                        int act, void* y, int y_ld, float* mean, float* rstd, float* scale, float* shift, float* workspace,
+                        void* stream);
+int mf_bn_train_backward(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                         const float* mean, const float* rstd, const float* scale, int act, void* dx, int dx_ld, void* dres,
+                         int dres_ld, float* dgamma, float* dbeta, float* workspace, void* stream);
+
 /* diagnostics: D[128,128] = A^T B with A [64,128] and B [64,128] fp16 row-major (reduction index = rows), computed with
  * MN-major tcgen05 operand descriptors - the operand form the weight-gradient GEMM of the training path needs */
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream);

@@ -1,0 +1,97 @@
+"""Backward building blocks of the convolutional layers (training path of SURVEY §8 rows R2/R3/R6; the reference gets
+them from cuDNN through autograd, engine/trainer.py:116-117). Both run on the hand-written tensor-core kernels:
+
+  * conv2d_wgrad : dW from NHWC fp16 activations and output gradients - `mf_conv2d_wgrad_nhwc_f16` (csrc/mf_wgrad.cu:
+                   tcgen05 GEMM whose MN-major operands come straight from im2col / tiled TMA boxes, split-K);
+  * conv2d_dgrad : dX of a stride-1 convolution = the forward implicit-GEMM kernel (csrc/mf_igemm2.cu) run on dY with the
+                   180-degree rotated, in/out-transposed weights and padding k-1-p (no new kernel; stride-2 layers need
+                   the four-parity decomposition and are not built yet).
+
+These are operators with parity tests (tests/test_gpu_train.py); the train-mode forward (batch-statistics BN) that would
+chain them into a full step is a later row, so KeypointDetector.forward still raises in training mode.
+"""
+import torch
+
+from . import engine
+from ._lib import call
+
+
+def _rows(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.half and t.dim() == 2 and t.is_contiguous()):
+        raise RuntimeError("%s must be a contiguous CUDA fp16 [pixels, channels] tensor (no CPU / PyTorch fallback)" % name)
+    return t
+
+
+def conv2d_wgrad(x_rows, dy_rows, B, H, W, k, stride=1, pad=0):
+    """x_rows [B*H*W, Cin], dy_rows [B*Ho*Wo, Cout] (NHWC fp16 rows) -> dW [Cout, Cin, k, k] fp32."""
+    x_rows, dy_rows = _rows(x_rows, "x_rows"), _rows(dy_rows, "dy_rows")
+    cin, cout = x_rows.shape[1], dy_rows.shape[1]
+    ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    if x_rows.shape[0] != B * H * W or dy_rows.shape[0] != B * ho * wo:
+        raise ValueError("conv2d_wgrad: row counts %d / %d do not match B=%d H=%d W=%d k=%d stride=%d pad=%d"
+                         % (x_rows.shape[0], dy_rows.shape[0], B, H, W, k, stride, pad))
+    dw = torch.empty(cout, cin, k, k, dtype=torch.float32, device=x_rows.device)
+    call("mf_conv2d_wgrad_nhwc_f16", x_rows.data_ptr(), cin, B, H, W, cin, dy_rows.data_ptr(), cout, cout, k, stride, pad,
+         dw.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return dw
+
+
+def conv2d_dgrad(dy_rows, weight, B, Ho, Wo, pad=0):
+    """dy_rows [B*Ho*Wo, Cout] fp16, weight [Cout, Cin, k, k] (stride-1 convolution with padding `pad`) ->
+    dx_rows [B*H*W, Cin] fp16 with H = Ho + k - 1 - 2 pad."""
+    dy_rows = _rows(dy_rows, "dy_rows")
+    cout, cin, k, k2 = weight.shape
+    if k != k2 or dy_rows.shape != (B * Ho * Wo, cout):
+        raise ValueError("conv2d_dgrad: shapes do not match")
+    if k - 1 - pad < 0:
+        raise NotImplementedError("conv2d_dgrad: pad > k - 1")
+    w_rot = weight.detach().float().flip(2, 3).transpose(0, 1).contiguous()          # [Cin, Cout, k, k]
+    P = engine.Plan(str(dy_rows.device))
+    dya = P.act(B, Ho, Wo, cout)
+    dya.buf = dy_rows                                                                  # zero-copy: the plan reads dY in place
+    dxa = P.conv(dya, w_rot, 1, k - 1 - pad, None, act=engine.ACT_NONE)
+    P.finalize()
+    P.run()
+    return dxa.buf[:, :cin] if dxa.buf.shape[1] != cin else dxa.buf
+
+
+class BatchNormTrain(object):
+    """Training-mode nn.BatchNorm2d / InPlaceABN over NHWC fp16 rows on the mf_bn_train_* kernels. forward() keeps what
+    backward() needs (raw input, activated output, batch statistics); running statistics are updated in place like torch."""
+
+    def __init__(self, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1, act=1, abs_gamma=False):
+        self.gamma, self.beta, self.running_mean, self.running_var = gamma, beta, running_mean, running_var
+        self.eps, self.momentum, self.act, self.abs_gamma = eps, momentum, act, abs_gamma
+        self.saved = None
+
+    def forward(self, x_rows, residual=None):
+        from ._lib import load
+        x_rows = _rows(x_rows, "x_rows")
+        M, C = x_rows.shape
+        dev = x_rows.device
+        y = torch.empty_like(x_rows)
+        stats = torch.empty(4, C, dtype=torch.float32, device=dev)            # mean, rstd, scale, shift
+        ws = torch.empty(load().mf_bn_train_workspace(M, C) // 4, dtype=torch.float32, device=dev)
+        call("mf_bn_train_forward", x_rows.data_ptr(), C, M, C, self.gamma.data_ptr(), self.beta.data_ptr(), self.eps,
+             self.momentum, 1 if self.abs_gamma else 0,
+             self.running_mean.data_ptr() if self.running_mean is not None else None,
+             self.running_var.data_ptr() if self.running_var is not None else None,
+             residual.data_ptr() if residual is not None else None, C, self.act, y.data_ptr(), C, stats[0].data_ptr(),
+             stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), ws.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+        self.saved = (x_rows, y, stats, ws, residual is not None)
+        return y
+
+    def backward(self, dy_rows):
+        """-> (dx_rows, dgamma, dbeta, dresidual_rows or None)"""
+        x_rows, y, stats, ws, has_res = self.saved
+        dy_rows = _rows(dy_rows, "dy_rows")
+        M, C = x_rows.shape
+        dx = torch.empty_like(x_rows)
+        dres = torch.empty_like(x_rows) if has_res else None
+        dg = torch.empty(2, C, dtype=torch.float32, device=x_rows.device)
+        call("mf_bn_train_backward", x_rows.data_ptr(), C, dy_rows.data_ptr(), C, y.data_ptr(), C, M, C, stats[0].data_ptr(),
+             stats[1].data_ptr(), stats[2].data_ptr(), self.act, dx.data_ptr(), C, dres.data_ptr() if has_res else None, C,
+             dg[0].data_ptr(), dg[1].data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        dgamma = dg[0] * torch.sign(self.gamma) if self.abs_gamma else dg[0]
+        return dx, dgamma, dg[1], dres

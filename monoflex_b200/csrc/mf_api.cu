@@ -179,6 +179,22 @@ int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int C
   return launch_conv_wgrad(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(dy), dy_ld, Cout, k,
                            stride, pad, dw, MF_STREAM(stream));
 }
+size_t mf_bn_train_workspace(long long M, int C) { return sizeof(float) * bn_train_workspace_floats(M, C); }
+int mf_bn_train_forward(const void* x, int x_ld, long long M, int C, const float* gamma, const float* beta, float eps,
+                        float momentum, int abs_gamma, float* running_mean, float* running_var, const void* res, int res_ld,
+                        int act, void* y, int y_ld, float* mean, float* rstd, float* scale, float* shift, float* workspace,
+                        void* stream) {
+  return launch_bn_train_forward(static_cast<const __half*>(x), x_ld, M, C, gamma, beta, eps, momentum, abs_gamma, running_mean,
+                                 running_var, static_cast<const __half*>(res), res_ld, act, static_cast<__half*>(y), y_ld, mean,
+                                 rstd, scale, shift, workspace, MF_STREAM(stream));
+}
+int mf_bn_train_backward(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                         const float* mean, const float* rstd, const float* scale, int act, void* dx, int dx_ld, void* dres,
+                         int dres_ld, float* dgamma, float* dbeta, float* workspace, void* stream) {
+  return launch_bn_train_backward(static_cast<const __half*>(x), x_ld, static_cast<const __half*>(dy), dy_ld,
+                                  static_cast<const __half*>(y), y_ld, M, C, mean, rstd, scale, act, static_cast<__half*>(dx),
+                                  dx_ld, static_cast<__half*>(dres), dres_ld, dgamma, dbeta, workspace, MF_STREAM(stream));
+}
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream) {
   return launch_mn_major_selftest(static_cast<const __half*>(a_km), static_cast<const __half*>(b_kn), d_mn, MF_STREAM(stream));
 }

@@ -28,6 +28,14 @@ int launch_loss_backward(const float* pred_cls, const float* hm, const float* pr
                          const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
                          const float* ws64, const float* grad_losses11, float* grad_cls, float* grad_reg, cudaStream_t st);
 int launch_mn_major_selftest(const __half* a_km, const __half* b_kn, float* d_mn, cudaStream_t st);
+size_t bn_train_workspace_floats(long long M, int C);
+int launch_bn_train_forward(const __half* x, int x_ld, long long M, int C, const float* gamma, const float* beta, float eps,
+                            float momentum, int abs_gamma, float* running_mean, float* running_var, const __half* res,
+                            int res_ld, int act, __half* y, int y_ld, float* mean, float* rstd, float* scale, float* shift,
+                            float* workspace, cudaStream_t st);
+int launch_bn_train_backward(const __half* x, int x_ld, const __half* dy, int dy_ld, const __half* y, int y_ld, long long M, int C,
+                             const float* mean, const float* rstd, const float* scale, int act, __half* dx, int dx_ld,
+                             __half* dres, int dres_ld, float* dgamma, float* dbeta, float* workspace, cudaStream_t st);
 #define MF_MAX_PEERS 16
 int launch_adamw_p2p(const unsigned long long* param_ptrs, const unsigned long long* grad_ptrs, int world, int rank,
                      unsigned long long mc_params, unsigned long long mc_grads, float* m, float* v, const float* chunk_lr,

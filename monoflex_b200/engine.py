@@ -82,7 +82,7 @@ class Plan(object):
 
     def finalize(self):
         for a in self.acts:
-            if a.owner is None:
+            if a.owner is None and a.buf is None:          # a.buf already set = caller-owned storage bound before finalize
                 if a.npar:
                     a.buf = torch.empty(a.M * a.C // 8, 8, dtype=torch.half, device=self.device)
                 else:

@@ -249,3 +249,72 @@ def test_conv_wgrad_tensor_core(case):
         ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, k, k), dy.float(), stride=s, padding=pad)
     err = (dw.cpu() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("case", [(2, 12, 20, 64, 64, 3, 1), (1, 9, 23, 64, 128, 1, 0), (2, 10, 12, 128, 64, 3, 1)])
+def test_conv_dgrad_via_forward_kernel(case):
+    """dX of a stride-1 conv = the forward tensor-core kernel on dY with rotated/transposed weights, vs
+    torch.nn.grad.conv2d_input on the same fp16-representable operands."""
+    from monoflex_b200 import backward
+    B, H, W, Cin, Cout, k, pad = case
+    gen = np.random.Generator(np.random.PCG64(sum(case) + 1))
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    w = torch.from_numpy((gen.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cout * k * k)).astype(np.float32)).half().float()
+    dy = torch.from_numpy(gen.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)).half()
+    dyr = dy.permute(0, 2, 3, 1).reshape(-1, Cout).contiguous().cuda()
+    dx = backward.conv2d_dgrad(dyr, w.cuda(), B, Ho, Wo, pad)
+    torch.cuda.synchronize()
+    assert dx.shape == (B * H * W, Cin)
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w, dy.float(), stride=1, padding=pad)
+    got = dx.float().cpu().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 1e-3      # fp16 output rounding
+
+
+def test_backward_python_wrappers_reject_cpu():
+    from monoflex_b200 import backward
+    with pytest.raises(RuntimeError):
+        backward.conv2d_wgrad(torch.zeros(64, 64, dtype=torch.half), torch.zeros(64, 64, dtype=torch.half).cuda(), 1, 8, 8, 1)
+
+
+@pytest.mark.parametrize("case", [(2, 12, 20, 64, 1, True), (1, 9, 23, 16, 1, False), (3, 7, 11, 512, 0, False),
+                                  (2, 16, 24, 256, 2, False), (8, 96, 320, 64, 1, True)])
+def test_batchnorm_train_forward_backward(case):
+    """train-mode BN (+ residual + activation) over NHWC fp16 rows vs torch (CPU fp32) batch_norm(training=True) and its
+    autograd, on the same fp16-representable inputs: output, running statistics, dx, dgamma, dbeta, dresidual."""
+    from monoflex_b200 import backward
+    import torch.nn.functional as F
+    B, H, W, C, act, use_res = case
+    gen = np.random.Generator(np.random.PCG64(sum(case[:4])))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    x = t(gen.standard_normal((B, C, H, W)) * 1.7 + 0.3).half().float()
+    res = t(gen.standard_normal((B, C, H, W))).half().float() if use_res else None
+    dy = t(gen.standard_normal((B, C, H, W))).half().float()
+    gamma, beta = t(gen.uniform(0.5, 1.5, C)), t(gen.standard_normal(C) * 0.1)
+    rm, rv = t(gen.standard_normal(C) * 0.1), t(gen.uniform(0.5, 1.5, C))
+    rows = lambda v: v.permute(0, 2, 3, 1).reshape(-1, C).contiguous().half().cuda()
+    bn = backward.BatchNormTrain(gamma.cuda(), beta.cuda(), rm.clone().cuda(), rv.clone().cuda(), act=act)
+    y = bn.forward(rows(x), rows(res) if use_res else None)
+    dx, dgamma, dbeta, dres = bn.backward(rows(dy))
+    torch.cuda.synchronize()
+    # reference
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if use_res else None
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    z = F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    if use_res:
+        z = z + rr
+    z = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.01)}[act](z)
+    back = lambda v: v.float().cpu().view(B, H, W, C).permute(0, 3, 1, 2)
+    yq = back(y)
+    assert (yq - z.detach()).abs().max().item() <= 2e-3 * z.detach().abs().max().item()          # fp16 output rounding
+    assert torch.allclose(bn.running_mean.cpu(), rm_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var.cpu(), rv_ref, rtol=1e-4, atol=1e-5)
+    # backward through the SAME activation mask the kernel saw (sign of the fp16 output): use autograd on the fp32 reference;
+    # elements within fp16 rounding of the ReLU kink may differ, so compare in the 1e-2-of-max norm on dx and tightly on sums
+    z.backward(dy)
+    assert (back(dx) - xr.grad).abs().max().item() <= 1e-2 * xr.grad.abs().max().item()
+    assert (dgamma.cpu() - gr.grad).abs().max().item() <= 2e-3 * gr.grad.abs().max().item()
+    assert (dbeta.cpu() - br.grad).abs().max().item() <= 2e-3 * br.grad.abs().max().item()
+    if use_res:
+        assert (back(dres) - rr.grad).abs().max().item() <= 1e-2 * rr.grad.abs().max().item()
