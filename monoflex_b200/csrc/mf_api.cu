@@ -48,9 +48,17 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, i
 
 // boundary B (exact-fp32 `_ext.dcn_v2_forward/backward` on NCHW tensors): kernels and launchers live in mf_dcn_f32.cu
 
+int g_tunable[16] = {0};   // experiment switches, see mf_set_tunable in include/monoflex_b200.h
+
+int igemm_block_n(int cout) {
+  if (cout <= 16) return 16;
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  return 128;
+}
+
 static int run_gemm(const IgemmParams& p, const void* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
   if (g_conv_impl == 1) return launch_simt_gemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
-  if (g_tunable[2] == 1) return launch_igemm(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);   // gen-1 kernel (A/B)
   return launch_igemm2(p, static_cast<const __half*>(wp), n_pad, k_pad, mode, st);
 }
 

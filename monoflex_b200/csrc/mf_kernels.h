@@ -36,7 +36,6 @@ struct IgemmParams {
 };
 
 int igemm_block_n(int cout);
-int launch_igemm(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar, const __half* wp, int n_pad, int k_pad,
                      int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
