@@ -129,6 +129,27 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
 int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
                              int stride, int pad, float* dw, void* stream);
 
+/* Backward twins of the HBM-bound layers (csrc/mf_bwd_misc.cu), NHWC fp16 rows unless noted:
+ *  maxpool2_bwd: MaxPool2d(2) (dla_dcn.py:238); gradient to the first maximum of each window (torch arg-max order).
+ *  upsample_bwd: depth-wise ConvTranspose2d(k = 2f, s = f, p = f/2) (dla_dcn.py:408-412): dx (nullable) and dw_taps [k*k, C]
+ *                fp32 (nullable; needs mf_upsample_bwd_workspace bytes of scratch); the skip input's gradient is dy itself.
+ *  sigmoid_clamp_bwd: sigmoid_hm (layers/utils.py:39-43), fp32: dx = dy * y (1 - y) where the clamp did not bind.
+ *  column_sum: out[c] = sum over rows (conv-bias gradients); scratch mf_column_sum_workspace bytes.
+ *  edge_gather_bwd: transpose of mf_edge_gather: ADDS the gradients of the two [B, K+2, 256] Conv1d inputs onto d_feat rows.
+ *  interleave2x2: out[b, 2i+py, 2j+px] = p{py}{px}[b, i, j] (recombines the parity sub-convolutions of a stride-2 dgrad). */
+int mf_maxpool2_bwd_nhwc_f16(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int x_ld, int dy_ld, int dx_ld,
+                             void* stream);
+size_t mf_upsample_bwd_workspace(int B, int Hi, int Wi, int C, int f);
+int mf_upsample_bwd_nhwc_f16(const void* x, const float* w_taps, const void* dy, void* dx, float* dw_taps, int B, int Hi, int Wi,
+                             int C, int f, int x_ld, int dy_ld, int dx_ld, float* workspace, void* stream);
+int mf_sigmoid_clamp_bwd(const float* y, const float* dy, float* dx, long long n, void* stream);
+size_t mf_column_sum_workspace(long long M, int C);
+int mf_column_sum_nhwc_f16(const void* x, int x_ld, long long M, int C, float* out, float* workspace, void* stream);
+int mf_edge_gather_bwd(const void* d_ea, const void* d_eb, int ch_a, int ch_b, const long long* edge_idx, void* d_feat, int feat_ld,
+                       int B, int H, int W, int K, int out_w, int out_h, void* stream);
+int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
+                              int B, int Hh, int Wh, int C, void* stream);
+
 /* Training-mode nn.BatchNorm2d(momentum 0.1) / InPlaceABN over NHWC fp16 rows (dla_dcn.py:76-79, detector_predictor.py:50,74;
  * eval mode is folded into the conv epilogues instead). x = raw conv output [M, x_ld], C channels (multiple of 8).
  * forward: batch mean / biased variance (deterministic two-level reduction), running-stat update like torch (unbiased

@@ -34,6 +34,14 @@ SIGNATURES = {
     "mf_focal_loss_forward": [_P, _P, _LL, _P, _P],
     "mf_focal_loss_backward": [_P, _P, _LL, _P, _P, _P],
     "mf_conv2d_wgrad_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P],
+    "mf_maxpool2_bwd_nhwc_f16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mf_upsample_bwd_workspace": [_I, _I, _I, _I, _I],
+    "mf_upsample_bwd_nhwc_f16": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mf_sigmoid_clamp_bwd": [_P, _P, _P, _LL, _P],
+    "mf_column_sum_workspace": [_LL, _I],
+    "mf_column_sum_nhwc_f16": [_P, _I, _LL, _I, _P, _P, _P],
+    "mf_edge_gather_bwd": [_P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mf_interleave2x2_nhwc_f16": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "mf_bn_train_workspace": [_LL, _I],
     "mf_bn_train_forward": [_P, _I, _LL, _I, _P, _P, _F, _F, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "mf_bn_train_backward": [_P, _I, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P],
@@ -68,7 +76,7 @@ def load():
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = args
-            fn.restype = _SZ if name in ("mf_dcn_v2_backward_workspace", "mf_bn_train_workspace") else _I
+            fn.restype = _SZ if name.endswith("_workspace") else _I
         _lib = lib
         for i, name in enumerate(("MF_DCN_EXTRA_SMEM", "MF_CONV_EXTRA_SMEM", "MF_UNUSED_2", "MF_NO_TMA_STORE", "MF_NO_TMA_IM2COL", "MF_TMA_SMALL_C", "MF_A_STATIONARY", "MF_DCN_WARPS_MODE", "MF_PDL", "MF_HEAD_CLUSTER")):     # experiments only
             if os.environ.get(name):

@@ -95,3 +95,82 @@ class BatchNormTrain(object):
              dg[0].data_ptr(), dg[1].data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
         dgamma = dg[0] * torch.sign(self.gamma) if self.abs_gamma else dg[0]
         return dx, dgamma, dg[1], dres
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def conv2d_dgrad_stride2(dy_rows, weight, B, Ho, Wo):
+    """dX of a 3x3 / stride-2 / pad-1 convolution (the level-entry convs, dla_dcn.py:69-79 with stride 2): the transposed
+    convolution splits by output parity (py, px) into four stride-1 convolutions of dY whose 3x3 kernels hold the 1, 2, 2
+    or 4 taps of W that reach that parity (zeros elsewhere) - run on the forward tensor-core kernel - and a 2x2 interleave.
+    dy_rows [B*Ho*Wo, Cout] fp16 -> dx_rows [B*(2Ho)*(2Wo), Cin] fp16."""
+    from ._lib import load
+    dy_rows = _rows(dy_rows, "dy_rows")
+    cout, cin, k, k2 = weight.shape
+    if (k, k2) != (3, 3) or dy_rows.shape != (B * Ho * Wo, cout):
+        raise NotImplementedError("conv2d_dgrad_stride2: only 3x3 / stride 2 / pad 1 is built")
+    w = weight.detach().float()
+    pad = 1
+    P = engine.Plan(str(dy_rows.device))
+    dya = P.act(B, Ho, Wo, cout)
+    dya.buf = dy_rows
+    parts = []
+    for py in (0, 1):
+        for px in (0, 1):
+            ws = torch.zeros(cin, cout, 3, 3, dtype=torch.float32, device=w.device)
+            for ky in range(3):
+                if (py + pad - ky) % 2:
+                    continue
+                ta = (py + pad - ky) // 2 + 1               # dX[2i+py] += dY[i + a] * W[ky], a = (py + pad - ky) / 2
+                for kx in range(3):
+                    if (px + pad - kx) % 2:
+                        continue
+                    tb = (px + pad - kx) // 2 + 1
+                    ws[:, :, ta, tb] = w[:, :, ky, kx].t()
+            parts.append(P.conv(dya, ws, 1, 1, None, act=engine.ACT_NONE))
+    P.finalize()
+    P.run()
+    dx = torch.empty(B * 2 * Ho * 2 * Wo, cin, dtype=torch.half, device=dy_rows.device)
+    call("mf_interleave2x2_nhwc_f16", parts[0].ptr(), parts[1].ptr(), parts[2].ptr(), parts[3].ptr(), parts[0].ld, dx.data_ptr(),
+         cin, B, Ho, Wo, cin, _st())
+    load()
+    return dx
+
+
+def maxpool2_backward(x_rows, dy_rows, B, H, W):
+    x_rows, dy_rows = _rows(x_rows, "x_rows"), _rows(dy_rows, "dy_rows")
+    C = x_rows.shape[1]
+    dx = torch.empty_like(x_rows)
+    call("mf_maxpool2_bwd_nhwc_f16", x_rows.data_ptr(), dy_rows.data_ptr(), dx.data_ptr(), B, H, W, C, C, C, C, _st())
+    return dx
+
+
+def upsample_backward(x_rows, w_taps, dy_rows, B, Hi, Wi, f):
+    """-> (dx_rows, dw_taps [k*k, C] fp32); the skip input's gradient is dy_rows itself."""
+    from ._lib import load
+    x_rows, dy_rows = _rows(x_rows, "x_rows"), _rows(dy_rows, "dy_rows")
+    C = x_rows.shape[1]
+    dx = torch.empty_like(x_rows)
+    dw = torch.empty(4 * f * f, C, dtype=torch.float32, device=x_rows.device)
+    ws = torch.empty(load().mf_upsample_bwd_workspace(B, Hi, Wi, C, f) // 4, dtype=torch.float32, device=x_rows.device)
+    call("mf_upsample_bwd_nhwc_f16", x_rows.data_ptr(), w_taps.data_ptr(), dy_rows.data_ptr(), dx.data_ptr(), dw.data_ptr(), B, Hi,
+         Wi, C, f, C, C, C, ws.data_ptr(), _st())
+    return dx, dw
+
+
+def sigmoid_clamp_backward(y, dy):
+    dx = torch.empty_like(y)
+    call("mf_sigmoid_clamp_bwd", y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(), _st())
+    return dx
+
+
+def column_sum(rows):
+    from ._lib import load
+    rows = _rows(rows, "rows")
+    M, C = rows.shape
+    out = torch.empty(C, dtype=torch.float32, device=rows.device)
+    ws = torch.empty(load().mf_column_sum_workspace(M, C) // 4, dtype=torch.float32, device=rows.device)
+    call("mf_column_sum_nhwc_f16", rows.data_ptr(), C, M, C, out.data_ptr(), ws.data_ptr(), _st())
+    return out

@@ -28,6 +28,18 @@ int launch_loss_backward(const float* pred_cls, const float* hm, const float* pr
                          const float* weights11, const float* dim_mean9, int B, int ncls, int M, int H, int W, int C,
                          const float* ws64, const float* grad_losses11, float* grad_cls, float* grad_reg, cudaStream_t st);
 int launch_mn_major_selftest(const __half* a_km, const __half* b_kn, float* d_mn, cudaStream_t st);
+int launch_maxpool2_bwd(const __half* x, const __half* dy, __half* dx, int B, int H, int W, int C, int x_ld, int dy_ld,
+                        int dx_ld, cudaStream_t st);
+size_t upsample_bwd_workspace_floats(int B, int Hi, int Wi, int C, int f);
+int launch_upsample_bwd(const __half* x, const float* w, const __half* dy, __half* dx, float* dw, int B, int Hi, int Wi, int C,
+                        int f, int x_ld, int dy_ld, int dx_ld, float* workspace, cudaStream_t st);
+int launch_sigmoid_clamp_bwd(const float* y, const float* dy, float* dx, long long n, cudaStream_t st);
+size_t column_sum_workspace_floats(long long M, int C);
+int launch_column_sum(const __half* x, int x_ld, long long M, int C, float* out, float* workspace, cudaStream_t st);
+int launch_edge_gather_bwd(const __half* d_ea, const __half* d_eb, int ch_a, int ch_b, const long long* edge_idx, __half* d_feat,
+                           int feat_ld, int B, int H, int W, int K, int out_w, int out_h, cudaStream_t st);
+int launch_interleave2x2(const __half* p00, const __half* p01, const __half* p10, const __half* p11, int part_ld, __half* out,
+                         int out_ld, int B, int Hh, int Wh, int C, cudaStream_t st);
 size_t bn_train_workspace_floats(long long M, int C);
 int launch_bn_train_forward(const __half* x, int x_ld, long long M, int C, const float* gamma, const float* beta, float eps,
                             float momentum, int abs_gamma, float* running_mean, float* running_var, const __half* res,

@@ -323,3 +323,88 @@ def test_batchnorm_train_forward_backward(case):
     assert (dbeta.cpu() - br.grad).abs().max().item() <= 2e-3 * br.grad.abs().max().item()
     if use_res:
         assert ((back(dres) - rr.grad).abs() * safe).max().item() <= 1e-2 * rr.grad.abs().max().item()
+
+
+def _rows_of(t4):
+    B, C, H, W = t4.shape
+    return t4.permute(0, 2, 3, 1).reshape(-1, C).contiguous().half().cuda()
+
+
+def _nchw_of(rows, B, H, W):
+    return rows.float().cpu().view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def test_conv_dgrad_stride2_parity_decomposition():
+    from monoflex_b200 import backward
+    gen = np.random.Generator(np.random.PCG64(91))
+    for (B, H, W, Cin, Cout) in ((2, 12, 20, 64, 128), (1, 16, 24, 128, 64)):
+        Ho, Wo = H // 2, W // 2
+        w = torch.from_numpy((gen.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cout * 9)).astype(np.float32)).half().float()
+        dy = torch.from_numpy(gen.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)).half().float()
+        dx = backward.conv2d_dgrad_stride2(_rows_of(dy), w.cuda(), B, Ho, Wo)
+        torch.cuda.synchronize()
+        ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w, dy, stride=2, padding=1)
+        assert (_nchw_of(dx, B, H, W) - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+def test_maxpool_upsample_sigmoid_colsum_backward():
+    """backward twins of the HBM-bound layers vs torch autograd (CPU fp32) on fp16-representable inputs."""
+    from monoflex_b200 import backward
+    import torch.nn.functional as F
+    gen = np.random.Generator(np.random.PCG64(92))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).half().float()
+    # MaxPool2d(2): distinct values (ties carry torch's first-index rule; continuous data has none)
+    B, C, H, W = 2, 64, 10, 12
+    x = t(gen.standard_normal((B, C, H, W))).requires_grad_(True)
+    dy = t(gen.standard_normal((B, C, H // 2, W // 2)))
+    F.max_pool2d(x, 2).backward(dy)
+    dx = backward.maxpool2_backward(_rows_of(x.detach()), _rows_of(dy), B, H, W)
+    assert torch.equal(_nchw_of(dx, B, H, W), x.grad)
+    # depth-wise ConvTranspose2d(k = 2f, s = f, p = f/2), f = 2 and 4
+    for f in (2, 4):
+        B, C, Hi, Wi = 2, 64, 6, 7
+        k = 2 * f
+        x = t(gen.standard_normal((B, C, Hi, Wi))).requires_grad_(True)
+        w = torch.from_numpy(gen.uniform(0.05, 0.5, (C, 1, k, k)).astype(np.float32)).requires_grad_(True)
+        dy = t(gen.standard_normal((B, C, Hi * f, Wi * f)))
+        F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=C).backward(dy)
+        w_taps = w.detach().view(C, k * k).t().contiguous().cuda()
+        dx, dw = backward.upsample_backward(_rows_of(x.detach()), w_taps, _rows_of(dy), B, Hi, Wi, f)
+        assert (_nchw_of(dx, B, Hi, Wi) - x.grad).abs().max().item() <= 2e-3 * x.grad.abs().max().item()
+        dw_ref = w.grad.view(C, k * k).t()
+        assert (dw.cpu() - dw_ref).abs().max().item() <= 1e-4 * dw_ref.abs().max().item()
+    # sigmoid_hm
+    z = t(gen.standard_normal((2, 3, 8, 10)) * 6).requires_grad_(True)
+    g = t(gen.standard_normal((2, 3, 8, 10)))
+    y = torch.clamp(torch.sigmoid(z), 1e-4, 1 - 1e-4)
+    y.backward(g)
+    got = backward.sigmoid_clamp_backward(y.detach().cuda(), g.cuda())
+    assert (got.cpu() - z.grad).abs().max().item() <= 1e-6
+    # column sum (conv-bias gradient)
+    m = t(gen.standard_normal((5000, 24)))
+    cs = backward.column_sum(m.half().cuda())
+    assert (cs.cpu() - m.sum(0)).abs().max().item() <= 1e-4 * m.sum(0).abs().max().item() + 1e-3
+
+
+def test_edge_gather_backward_is_the_transpose():
+    """<edge_gather(feat), d_e> == <feat, edge_gather_bwd(d_e)> (adjoint identity) with the real 832-entry border list."""
+    from monoflex_b200._lib import call, stream
+    from monoflex_b200 import synthetic as syn
+    gen = np.random.Generator(np.random.PCG64(93))
+    B, H, W, K = 2, 96, 320, 832
+    idx, n, _ = syn.edge_indices()
+    edge = idx.unsqueeze(0).repeat(B, 1, 1).cuda()
+    feat = torch.from_numpy((gen.standard_normal((B * H * W, 512)) * 0.5).astype(np.float32)).half().cuda()
+    ea = torch.zeros(B, K + 2, 256, dtype=torch.half, device="cuda")
+    eb = torch.zeros_like(ea)
+    call("mf_edge_gather", feat.data_ptr(), 512, 0, 256, edge.data_ptr(), ea.data_ptr(), eb.data_ptr(), B, H, W, K, 320, 96, stream())
+    da = torch.from_numpy(gen.standard_normal((B, K + 2, 256)).astype(np.float32)).half().cuda()
+    db = torch.from_numpy(gen.standard_normal((B, K + 2, 256)).astype(np.float32)).half().cuda()
+    dfeat = torch.zeros_like(feat)
+    call("mf_edge_gather_bwd", da.data_ptr(), db.data_ptr(), 0, 256, edge.data_ptr(), dfeat.data_ptr(), 512, B, H, W, K, 320, 96,
+         stream())
+    lhs = (ea.double() * da.double()).sum() + (eb.double() * db.double()).sum()
+    rhs = (feat.double() * dfeat.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 2e-3 * abs(lhs.item())
+    touched = (dfeat != 0).any(1).sum().item()
+    assert 0 < touched <= 4 * B * K
