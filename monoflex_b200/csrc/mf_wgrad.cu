@@ -17,22 +17,30 @@
 namespace mf {
 
 static constexpr int WG_BK = 64;                        // pixels per k block
-static constexpr int WG_SLOT = WG_BK * 128;             // one [64 pixels x 64 channels] fp16 box = 8 KB
 static constexpr int WG_STAGES = 6;
+// Narrow layers (Cin or Cout = 16 / 32: level0 / level1 of DLA-34) use narrower boxes: an A slot is AW = min(Cin, 64)
+// channels wide (128 / AW slots per M tile), a B box BW = min(Cout, 64); the TMA swizzle and the descriptor layout type
+// follow the box width (128B / 64B / 32B), LBO = box bytes, SBO = 8 rows of the box.
+MF_DEVINL constexpr uint32_t wg_layout(int width) { return width == 64 ? 2u : (width == 32 ? 4u : 6u); }
 
 struct WgradParams {
   int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad;
-  int nslots;            // taps * Cin / 64
+  int nslots;            // taps * Cin / AW
   int ntm, ntn;          // M tiles (slot pairs), N tiles
   int nkb;               // ceil(B*Ho*Wo / 64)
   int splits;            // K splits per tile
   float* dw;             // [Cout, Cin, k, k] fp32, zero-initialised by the launcher
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int AW, int BW>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgradParams p) {
-  constexpr int A_STAGE = 2 * WG_SLOT, B_STAGE = (BLOCK_N / 64) * WG_SLOT;
+  constexpr int SPT = 128 / AW;                            // A slots per M tile
+  constexpr int A_BOX = WG_BK * AW * 2, B_BOX = WG_BK * BW * 2;
+  constexpr int A_STAGE = SPT * A_BOX;                     // = 16 KB
+  constexpr int NB = BLOCK_N / BW;
+  constexpr int B_STAGE = NB * B_BOX < 1024 ? 1024 : NB * B_BOX;
+  constexpr int TCOLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -44,7 +52,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nitems = p.ntm * p.ntn * p.splits;
-  const int HoWo = p.Ho * p.Wo, cblocks = p.Cin / 64;
+  const int HoWo = p.Ho * p.Wo, cblocks = p.Cin / AW;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_dy);
@@ -52,7 +60,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     mbar_init(acc_full, 1); mbar_init(acc_empty, 128);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_ptr_smem, BLOCK_N < 32 ? 32 : BLOCK_N);
+  if (warp == 5) tmem_alloc(tmem_ptr_smem, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -77,30 +85,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         int mt, nt, kb_lo, kb_hi;
         decode(item, mt, nt, kb_lo, kb_hi);
-        int s_tap[2], s_c0[2];
+        int s_tap[SPT], s_c0[SPT];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          int slot = 2 * mt + h;
-          if (slot >= p.nslots) slot = p.nslots - 1;             // dummy half (its rows are discarded by the epilogue)
+        for (int h = 0; h < SPT; ++h) {
+          int slot = SPT * mt + h;
+          if (slot >= p.nslots) slot = p.nslots - 1;             // dummy slot (its rows are discarded by the epilogue)
           s_tap[h] = slot / cblocks;
-          s_c0[h] = (slot - s_tap[h] * cblocks) * 64;
+          s_c0[h] = (slot - s_tap[h] * cblocks) * AW;
         }
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           const int p0 = kb * WG_BK;                              // first output pixel of the block
           const int n = p0 / HoWo, rem = p0 - n * HoWo;
           const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + NB * B_BOX);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < SPT; ++h) {
             const int ky = s_tap[h] / p.k, kx = s_tap[h] - ky * p.k;
-            tma_load_im2col_4d(smem_u32(a_smem + stage * A_STAGE + h * WG_SLOT), &tmap_x, &full_bar[stage], s_c0[h],
+            tma_load_im2col_4d(smem_u32(a_smem + stage * A_STAGE + h * A_BOX), &tmap_x, &full_bar[stage], s_c0[h],
                                ox * p.stride - p.pad, oy * p.stride - p.pad, n, static_cast<uint16_t>(kx),
                                static_cast<uint16_t>(ky));
           }
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(smem_u32(b_smem + stage * B_STAGE + j * WG_SLOT), &tmap_dy, &full_bar[stage], nt * BLOCK_N + j * 64, p0);
+          for (int j = 0; j < NB; ++j)
+            tma_load_2d(smem_u32(b_smem + stage * B_STAGE + j * B_BOX), &tmap_dy, &full_bar[stage], nt * BLOCK_N + j * BW, p0);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -109,8 +117,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     // ================================================================ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N) | (1u << 15) | (1u << 16);      // A and B MN-major
-      const uint64_t a_d0 = umma_desc_kmajor(smem_u32(a_smem), WG_SLOT, 1024, 2);
-      const uint64_t b_d0 = umma_desc_kmajor(smem_u32(b_smem), WG_SLOT, 1024, 2);
+      const uint64_t a_d0 = umma_desc_kmajor(smem_u32(a_smem), A_BOX, 16 * AW, wg_layout(AW));
+      const uint64_t b_d0 = umma_desc_kmajor(smem_u32(b_smem), B_BOX, 16 * BW, wg_layout(BW));
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
@@ -123,9 +131,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           tc_fence_after();
           const uint64_t a_off = static_cast<uint64_t>((stage * A_STAGE) >> 4), b_off = static_cast<uint64_t>((stage * B_STAGE) >> 4);
 #pragma unroll
-          for (int k4 = 0; k4 < WG_BK / 16; ++k4)                 // 16 pixels = two 8-row groups = 2048 B per MMA
-            umma_f16(tmem_base, a_d0 + a_off + static_cast<uint64_t>(k4 * 128), b_d0 + b_off + static_cast<uint64_t>(k4 * 128),
-                     idesc, (kb > kb_lo || k4 != 0) ? 1u : 0u);
+          for (int k4 = 0; k4 < WG_BK / 16; ++k4)                 // 16 pixels = two 8-row groups (2 * SBO) per MMA
+            umma_f16(tmem_base, a_d0 + a_off + static_cast<uint64_t>(k4 * ((2 * 16 * AW) >> 4)),
+                     b_d0 + b_off + static_cast<uint64_t>(k4 * ((2 * 16 * BW) >> 4)), idesc, (kb > kb_lo || k4 != 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -141,20 +149,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       int mt, nt, kb_lo, kb_hi;
       decode(item, mt, nt, kb_lo, kb_hi);
-      const int slot = 2 * mt + (row >> 6);
+      const int slot = SPT * mt + row / AW;
       const bool valid = slot < p.nslots && kb_hi > kb_lo;
       const int tap = valid ? slot / cblocks : 0;
-      const int ci = valid ? (slot - tap * cblocks) * 64 + (row & 63) : 0;
+      const int ci = valid ? (slot - tap * cblocks) * AW + (row % AW) : 0;
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
+      constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+      for (int c = 0; c < BLOCK_N; c += CH) {
+        uint32_t r[CH];
+        if constexpr (CH == 32) tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+        else tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CH; ++j) {
             const int co = nt * BLOCK_N + c + j;
             if (co < p.Cout) atomicAdd(p.dw + (static_cast<long long>(co) * p.Cin + ci) * taps + tap, __uint_as_float(r[j]));
           }
@@ -166,7 +176,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -184,16 +194,24 @@ static void* wg_driver_fn(const char* name) {
   return ptr;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int AW, int BW>
 static int launch_wgrad_cfg(const CUtensorMap& tx, const CUtensorMap& tdy, const WgradParams& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = WG_STAGES * (2 * WG_SLOT + (BLOCK_N / 64) * WG_SLOT) + 1024 + 1024;
+  constexpr int B_ST = (BLOCK_N / BW) * WG_BK * BW * 2 < 1024 ? 1024 : (BLOCK_N / BW) * WG_BK * BW * 2;
+  constexpr int SMEM = WG_STAGES * (WG_BK * 128 * 2 + B_ST) + 1024 + 1024;
   static bool attr = false;
   if (!attr) {
-    if (check_cuda(cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "wgrad smem")) return -1;
+    if (check_cuda(cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, AW, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM), "wgrad smem")) return -1;
     attr = true;
   }
-  wgrad_kernel<BLOCK_N><<<grid, 192, SMEM, st>>>(tx, tdy, p);
+  wgrad_kernel<BLOCK_N, AW, BW><<<grid, 192, SMEM, st>>>(tx, tdy, p);
   return check_cuda(cudaGetLastError(), "conv wgrad launch");
+}
+template <int AW>
+static int launch_wgrad_n(int bn, const CUtensorMap& tx, const CUtensorMap& tdy, const WgradParams& p, int grid, cudaStream_t st) {
+  if (bn == 128) return launch_wgrad_cfg<128, AW, 64>(tx, tdy, p, grid, st);
+  if (bn == 64) return launch_wgrad_cfg<64, AW, 64>(tx, tdy, p, grid, st);
+  if (bn == 32) return launch_wgrad_cfg<32, AW, 32>(tx, tdy, p, grid, st);
+  return launch_wgrad_cfg<16, AW, 16>(tx, tdy, p, grid, st);
 }
 
 // x: [B*H*W, x_ld] fp16 NHWC rows; dy: [B*Ho*Wo, dy_ld] fp16 rows; dw: [Cout, Cin, k, k] fp32 (overwritten)
@@ -202,11 +220,15 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
   static PFN_encTiledW enc = reinterpret_cast<PFN_encTiledW>(wg_driver_fn("cuTensorMapEncodeTiled"));
   static PFN_encIm2colW enc2 = reinterpret_cast<PFN_encIm2colW>(wg_driver_fn("cuTensorMapEncodeIm2col"));
   if (!enc || !enc2) { set_error("conv wgrad: tensor-map driver entry points unavailable"); return -1; }
-  if (Cin % 64 != 0 || Cout % 64 != 0 || x_ld % 8 != 0 || dy_ld % 8 != 0 || k < 1 || k > 7 || stride < 1 || stride > 8 ||
+  const bool cin_ok = Cin == 16 || Cin == 32 || (Cin > 0 && Cin % 64 == 0);
+  const bool cout_ok = Cout == 16 || Cout == 32 || (Cout > 0 && Cout % 64 == 0);
+  if (!cin_ok || !cout_ok || x_ld % 8 != 0 || dy_ld % 8 != 0 || k < 1 || k > 7 || stride < 1 || stride > 8 ||
       (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) {
-    set_error("conv wgrad: needs Cin, Cout multiples of 64 and 16-byte aligned rows (Cin=%d Cout=%d k=%d s=%d)", Cin, Cout, k, stride);
+    set_error("conv wgrad: needs Cin, Cout in {16, 32, multiples of 64} and 16-byte aligned rows (Cin=%d Cout=%d k=%d s=%d)", Cin,
+              Cout, k, stride);
     return -1;
   }
+  const int aw = Cin < 64 ? Cin : 64, bw = Cout < 64 ? Cout : 64;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
@@ -214,9 +236,10 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
   p.Wo = (W + 2 * pad - k) / stride + 1;
   if (p.Ho < 1 || p.Wo < 1) { set_error("conv wgrad: empty output"); return -1; }
   const long long Mout = static_cast<long long>(B) * p.Ho * p.Wo;
-  const int bn = Cout % 128 == 0 ? 128 : 64;
-  p.nslots = k * k * (Cin / 64);
-  p.ntm = (p.nslots + 1) / 2;
+  const int bn = Cout < 64 ? Cout : (Cout % 128 == 0 ? 128 : 64);
+  const int spt = 128 / aw;
+  p.nslots = k * k * (Cin / aw);
+  p.ntm = (p.nslots + spt - 1) / spt;
   p.ntn = Cout / bn;
   p.nkb = static_cast<int>((Mout + WG_BK - 1) / WG_BK);
   p.dw = dw;
@@ -234,17 +257,19 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(x_ld) * 2, static_cast<cuuint64_t>(x_ld) * 2 * W, static_cast<cuuint64_t>(x_ld) * 2 * W * H};
     int lower[2] = {-pad, -pad}, upper[2] = {pad - (k - 1), pad - (k - 1)};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
-    if (enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(x), gdim, gstr, lower, upper, 64, WG_BK, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const CUtensorMapSwizzle swa = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(x), gdim, gstr, lower, upper, static_cast<cuuint32_t>(aw),
+             WG_BK, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swa, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { set_error("conv wgrad: im2col map failed"); return -1; }
   }
   {
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Cout), static_cast<cuuint64_t>(Mout)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(dy_ld) * 2};
-    cuuint32_t box[2] = {64, WG_BK};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(bw), WG_BK};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle swb = bw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     if (enc(&tdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            swb, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       set_error("conv wgrad: dY map failed");
       return -1;
     }
@@ -252,7 +277,9 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
   if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * Cout * Cin * k * k, st), "conv wgrad memset")) return -1;
   const int nitems = tiles * splits;
   const int grid = nitems < nsm ? nitems : nsm;
-  return bn == 128 ? launch_wgrad_cfg<128>(tx, tdy, p, grid, st) : launch_wgrad_cfg<64>(tx, tdy, p, grid, st);
+  if (aw == 64) return launch_wgrad_n<64>(bn, tx, tdy, p, grid, st);
+  if (aw == 32) return launch_wgrad_n<32>(bn, tx, tdy, p, grid, st);
+  return launch_wgrad_n<16>(bn, tx, tdy, p, grid, st);
 }
 
 }  // namespace mf

@@ -227,6 +227,11 @@ def test_fused_gradient_exchange_multi_gpu():
     (1, 9, 23, 64, 256, 1, 1, 0),        # 1x1, two N tiles
     (2, 10, 12, 192, 64, 3, 1, 1),       # odd number of 64-channel slots
     (8, 96, 320, 64, 64, 3, 1, 1),       # full-size level-2 layer: long split-K reduction
+    (2, 20, 36, 16, 16, 3, 1, 1),        # level0: 32-byte boxes for both operands, 8 taps per M tile
+    (2, 20, 36, 16, 32, 3, 2, 1),        # level1 entry: stride 2, N = 32
+    (1, 18, 26, 32, 64, 3, 2, 1),        # level2 entry: 64-byte A boxes, 128-byte B boxes
+    (2, 12, 14, 32, 32, 3, 1, 1),        # level1 second conv
+    (1, 10, 22, 32, 64, 1, 1, 0),        # project 1x1 after max-pool
 ])
 def test_conv_wgrad_tensor_core(case):
     """dW of a convolution from NHWC fp16 activations / output gradients (MN-major tcgen05 operands, split-K) vs
