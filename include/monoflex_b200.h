@@ -150,6 +150,17 @@ int mf_edge_gather_bwd(const void* d_ea, const void* d_eb, int ch_a, int ch_b, c
 int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
                               int B, int Hh, int Wh, int C, void* stream);
 
+/* Backward of the fused DCNv2 layer on the NHWC fp16 path (_DCNv2.backward dcn_v2.py:35-51; 3x3, stride 1, pad 1, one group).
+ * The two GEMMs are existing kernels: gcol = 1x1 conv of dY with W^T (mf_conv2d_nhwc_f16), dW = mf_conv2d_wgrad_nhwc_f16
+ * with k = 1 on `cols`. offmask: the forward's [M, om_ld >= 27] fp32 rows (18 offsets, 9 sigmoid-ed masks).
+ *  sample_cols: cols[p, tap*C + c] = mask * bilinear sample (fp16 [M, 9C]) - the forward's operand tiles written out.
+ *  col2im: dx (zeroed, then half2 atomics) and d_offmask [M, 32] fp32 = gradients of the offset conv's PRE-activation
+ *          outputs (offsets; masks through m (1 - m)); gcol fp16 [M, 9C] (k = tap*C + c). */
+int mf_dcn_sample_cols_nhwc_f16(const void* x, int x_ld, const float* offmask, int om_ld, void* cols, int B, int H, int W, int C,
+                                void* stream);
+int mf_dcn_col2im_nhwc_f16(const void* x, int x_ld, const float* offmask, int om_ld, const void* gcol, void* dx, int dx_ld,
+                           float* d_offmask, int B, int H, int W, int C, void* stream);
+
 /* Training-mode nn.BatchNorm2d(momentum 0.1) / InPlaceABN over NHWC fp16 rows (dla_dcn.py:76-79, detector_predictor.py:50,74;
  * eval mode is folded into the conv epilogues instead). x = raw conv output [M, x_ld], C channels (multiple of 8).
  * forward: batch mean / biased variance (deterministic two-level reduction), running-stat update like torch (unbiased

@@ -174,3 +174,34 @@ def column_sum(rows):
     ws = torch.empty(load().mf_column_sum_workspace(M, C) // 4, dtype=torch.float32, device=rows.device)
     call("mf_column_sum_nhwc_f16", rows.data_ptr(), C, M, C, out.data_ptr(), ws.data_ptr(), _st())
     return out
+
+
+def dcn_backward(x_rows, offmask_rows, dy_rows, weight, B, H, W):
+    """Backward of the fused DCNv2 layer (3x3, stride 1, pad 1) on NHWC fp16 rows.
+    x_rows [M, C], offmask_rows [M, 32] fp32 (the forward's offset-conv output: 18 offsets, 9 sigmoid-ed masks),
+    dy_rows [M, Cout], weight [Cout, C, 3, 3] ->
+    (dx_rows [M, C] fp16, d_offmask_rows [M, 32] fp32 = gradient of the offset conv's pre-activation output,
+     dW [Cout, C, 3, 3] fp32, dbias [Cout] fp32)."""
+    x_rows, dy_rows = _rows(x_rows, "x_rows"), _rows(dy_rows, "dy_rows")
+    M, C = x_rows.shape
+    cout = weight.shape[0]
+    if weight.shape != (cout, C, 3, 3) or dy_rows.shape != (M, cout) or offmask_rows.shape != (M, 32) or M != B * H * W:
+        raise ValueError("dcn_backward: shapes do not match")
+    dev = x_rows.device
+    # grad columns: a 1x1 forward conv of dY with W^T, output channel n = tap * C + c
+    wt = weight.detach().float().permute(2, 3, 1, 0).reshape(9 * C, cout, 1, 1).contiguous()
+    P = engine.Plan(str(dev))
+    dya = P.act(B, H, W, cout)
+    dya.buf = dy_rows
+    gcol = P.conv(dya, wt, 1, 0, None, act=engine.ACT_NONE)
+    P.finalize()
+    P.run()
+    cols = torch.empty(M, 9 * C, dtype=torch.half, device=dev)
+    call("mf_dcn_sample_cols_nhwc_f16", x_rows.data_ptr(), C, offmask_rows.data_ptr(), 32, cols.data_ptr(), B, H, W, C, _st())
+    dw9 = conv2d_wgrad(cols, dy_rows, B, H, W, 1, 1, 0)                                   # [Cout, 9C, 1, 1]
+    dw = dw9.view(cout, 3, 3, C).permute(0, 3, 1, 2).contiguous()
+    dx = torch.empty_like(x_rows)
+    dom = torch.empty(M, 32, dtype=torch.float32, device=dev)
+    call("mf_dcn_col2im_nhwc_f16", x_rows.data_ptr(), C, offmask_rows.data_ptr(), 32, gcol.ptr(), dx.data_ptr(), C, dom.data_ptr(),
+         B, H, W, C, _st())
+    return dx, dom, dw, column_sum(dy_rows)

@@ -40,6 +40,10 @@ int launch_edge_gather_bwd(const __half* d_ea, const __half* d_eb, int ch_a, int
                            int feat_ld, int B, int H, int W, int K, int out_w, int out_h, cudaStream_t st);
 int launch_interleave2x2(const __half* p00, const __half* p01, const __half* p10, const __half* p11, int part_ld, __half* out,
                          int out_ld, int B, int Hh, int Wh, int C, cudaStream_t st);
+int launch_dcn_sample_cols(const __half* x, int x_ld, const float* om, int om_ld, __half* cols, int B, int H, int W, int C,
+                           cudaStream_t st);
+int launch_dcn_col2im(const __half* x, int x_ld, const float* om, int om_ld, const __half* gcol, __half* dx, int dx_ld, float* dom,
+                      int B, int H, int W, int C, cudaStream_t st);
 size_t bn_train_workspace_floats(long long M, int C);
 int launch_bn_train_forward(const __half* x, int x_ld, long long M, int C, const float* gamma, const float* beta, float eps,
                             float momentum, int abs_gamma, float* running_mean, float* running_var, const __half* res,

@@ -413,3 +413,34 @@ def test_edge_gather_backward_is_the_transpose():
     assert abs(lhs.item() - rhs.item()) <= 2e-3 * abs(lhs.item())
     touched = (dfeat != 0).any(1).sum().item()
     assert 0 < touched <= 4 * B * K
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 10, 12), (1, 128, 64, 8, 9), (1, 512, 256, 6, 10)])
+def test_dcn_backward_tensor_core_path(case):
+    """fp16 NHWC DCN backward (two existing tensor-core GEMMs + the sampling / col2im kernels) vs torch autograd through
+    the CPU oracle's dcn_v2_forward with mask = sigmoid(pre): dX, d offsets, d mask pre-activation, dW, dB."""
+    from monoflex_b200 import backward
+    B, C, Co, H, W = case
+    gen = np.random.Generator(np.random.PCG64(sum(case)))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    x = t(gen.standard_normal((B, C, H, W))).half().float()
+    w = t(gen.standard_normal((Co, C, 3, 3)) / np.sqrt(9 * C)).half().float()
+    bias = t(gen.standard_normal(Co) * 0.1)
+    off = t(gen.standard_normal((B, 18, H, W)) * 1.5)
+    pre = t(gen.standard_normal((B, 9, H, W)))
+    dy = t(gen.standard_normal((B, Co, H, W))).half().float()
+    leaves = [v.clone().requires_grad_(True) for v in (x, w, bias, off, pre)]
+    mo.dcn_v2_forward(leaves[0], leaves[1], leaves[2], leaves[3], torch.sigmoid(leaves[4])).backward(dy)
+    om = torch.zeros(B * H * W, 32)
+    om[:, :18] = off.permute(0, 2, 3, 1).reshape(-1, 18)
+    om[:, 18:27] = torch.sigmoid(pre).permute(0, 2, 3, 1).reshape(-1, 9)
+    dx, dom, dw, db = backward.dcn_backward(_rows_of(x), om.cuda(), _rows_of(dy), w.cuda(), B, H, W)
+    torch.cuda.synchronize()
+    rel = lambda a, b: (a - b).abs().max().item() / b.abs().max().item()
+    assert rel(_nchw_of(dx, B, H, W), leaves[0].grad) < 1e-2               # fp16 grad columns + half2 atomics
+    assert rel(dw.cpu(), leaves[1].grad) < 3e-3                            # fp16 sampled columns
+    assert rel(db.cpu(), leaves[2].grad) < 1e-4
+    dom = dom.cpu().view(B, H, W, 32).permute(0, 3, 1, 2)
+    assert rel(dom[:, :18], leaves[3].grad) < 1e-2
+    assert rel(dom[:, 18:27], leaves[4].grad) < 1e-2
+    assert dom[:, 27:].abs().sum().item() == 0
