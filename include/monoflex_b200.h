@@ -128,6 +128,9 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
  * tcgen05 GEMM with MN-major operands fed by im2col / tiled TMA, split-K with fp32 atomics (summation order not fixed). */
 int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
                              int stride, int pad, float* dw, void* stream);
+/* same with a rectangular kernel / padding (the edge fusion's Conv1d(256, 256, 3) is a 1 x 3 convolution over [B, 1, K+2, 256]) */
+int mf_conv2d_wgrad_rect_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int kh,
+                                  int kw, int stride, int pad_h, int pad_w, float* dw, void* stream);
 
 /* Backward twins of the HBM-bound layers (csrc/mf_bwd_misc.cu), NHWC fp16 rows unless noted:
  *  maxpool2_bwd: MaxPool2d(2) (dla_dcn.py:238); gradient to the first maximum of each window (torch arg-max order).
@@ -147,6 +150,11 @@ size_t mf_column_sum_workspace(long long M, int C);
 int mf_column_sum_nhwc_f16(const void* x, int x_ld, long long M, int C, float* out, float* workspace, void* stream);
 int mf_edge_gather_bwd(const void* d_ea, const void* d_eb, int ch_a, int ch_b, const long long* edge_idx, void* d_feat, int feat_ld,
                        int B, int H, int W, int K, int out_w, int out_h, void* stream);
+/* backward of mf_edge_head_add: d_t [B, K, 256] fp16 (0 past edge_len), dw [n_out, 256] and dbias [n_out] fp32 (overwritten;
+ * fp32 atomics), from d_out = gradient of the fp32 NCHW map the forward added into */
+int mf_edge_head_add_bwd(const void* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
+                         const float* d_out, int out_ctot, int out_ch0, void* d_t, float* dw, float* dbias, int B, int K, int H,
+                         int W, void* stream);
 int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
                               int B, int Hh, int Wh, int C, void* stream);
 

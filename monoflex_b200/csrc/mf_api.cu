@@ -184,8 +184,13 @@ int mf_focal_loss_backward(const float* pred, const float* target, long long n, 
 }
 int mf_conv2d_wgrad_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int k,
                              int stride, int pad, float* dw, void* stream) {
-  return launch_conv_wgrad(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(dy), dy_ld, Cout, k,
-                           stride, pad, dw, MF_STREAM(stream));
+  return launch_conv_wgrad(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(dy), dy_ld, Cout, k, k,
+                           stride, pad, pad, dw, MF_STREAM(stream));
+}
+int mf_conv2d_wgrad_rect_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* dy, int dy_ld, int Cout, int kh,
+                                  int kw, int stride, int pad_h, int pad_w, float* dw, void* stream) {
+  return launch_conv_wgrad(static_cast<const __half*>(x), x_ld, B, H, W, Cin, static_cast<const __half*>(dy), dy_ld, Cout, kh, kw,
+                           stride, pad_h, pad_w, dw, MF_STREAM(stream));
 }
 int mf_maxpool2_bwd_nhwc_f16(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int x_ld, int dy_ld, int dx_ld,
                              void* stream) {
@@ -209,6 +214,12 @@ int mf_edge_gather_bwd(const void* d_ea, const void* d_eb, int ch_a, int ch_b, c
                        int B, int H, int W, int K, int out_w, int out_h, void* stream) {
   return launch_edge_gather_bwd(static_cast<const __half*>(d_ea), static_cast<const __half*>(d_eb), ch_a, ch_b, edge_idx,
                                 static_cast<__half*>(d_feat), feat_ld, B, H, W, K, out_w, out_h, MF_STREAM(stream));
+}
+int mf_edge_head_add_bwd(const void* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
+                         const float* d_out, int out_ctot, int out_ch0, void* d_t, float* dw, float* dbias, int B, int K, int H,
+                         int W, void* stream) {
+  return launch_edge_head_add_bwd(static_cast<const __half*>(t), w, n_out, edge_idx, edge_len, d_out, out_ctot, out_ch0,
+                                  static_cast<__half*>(d_t), dw, dbias, B, K, H, W, MF_STREAM(stream));
 }
 int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
                               int B, int Hh, int Wh, int C, void* stream) {

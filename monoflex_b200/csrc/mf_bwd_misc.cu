@@ -295,6 +295,48 @@ int launch_edge_gather_bwd(const __half* d_ea, const __half* d_eb, int ch_a, int
   return check_cuda(cudaGetLastError(), "edge_gather_bwd");
 }
 
+// ---------------------------------------------------------------- edge_head_add backward (detector_predictor.py:155-158)
+// forward: out[b, ch0 + o, ey, ex] += bias[o] + sum_c t[b, e, c] * w[o, c] for the first edge_len[b] border positions e.
+// backward: d_t[b, e, c] = sum_o g[o] w[o, c] (0 past edge_len), dw[o, c] += g[o] t[b, e, c], dbias[o] += g[o], with
+// g[o] = d_out[b, ch0 + o, ey, ex]. One warp per (b, e); dw / dbias by fp32 atomics (zeroed by the launcher).
+__global__ void edge_head_add_bwd_kernel(const __half* __restrict__ t, const float* __restrict__ w, int n_out,
+                                         const long long* __restrict__ edge_idx, const long long* __restrict__ edge_len,
+                                         const float* __restrict__ d_out, int out_ctot, int out_ch0, __half* __restrict__ d_t,
+                                         float* __restrict__ dw, float* __restrict__ dbias, int B, int K, int H, int W) {
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  const int b = warp / K, e = warp - b * K;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  if (e < edge_len[b]) {
+    float tv[8];
+    bm_unpack8(__ldg(reinterpret_cast<const uint4*>(t + static_cast<long long>(warp) * 256 + lane * 8)), tv);
+    const long long ex = edge_idx[(static_cast<long long>(b) * K + e) * 2], ey = edge_idx[(static_cast<long long>(b) * K + e) * 2 + 1];
+    for (int o = 0; o < n_out; ++o) {
+      const float g = __ldg(d_out + ((static_cast<long long>(b) * out_ctot + out_ch0 + o) * H + ey) * W + ex);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        acc[q] += g * __ldg(w + o * 256 + lane * 8 + q);
+        atomicAdd(dw + o * 256 + lane * 8 + q, g * tv[q]);
+      }
+      if (lane == 0) atomicAdd(dbias + o, g);
+    }
+  }
+  *reinterpret_cast<uint4*>(d_t + static_cast<long long>(warp) * 256 + lane * 8) = bm_pack8(acc);
+}
+int launch_edge_head_add_bwd(const __half* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
+                             const float* d_out, int out_ctot, int out_ch0, __half* d_t, float* dw, float* dbias, int B, int K,
+                             int H, int W, cudaStream_t st) {
+  if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * 256, st), "edge_head_add_bwd memset")) return -1;
+  if (check_cuda(cudaMemsetAsync(dbias, 0, sizeof(float) * n_out, st), "edge_head_add_bwd memset")) return -1;
+  const long long threads = static_cast<long long>(B) * K * 32;
+  (void)launch_k(edge_head_add_bwd_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, t, w, n_out,
+                 edge_idx, edge_len, d_out, out_ctot, out_ch0, d_t, dw, dbias, B, K, H, W);
+  return check_cuda(cudaGetLastError(), "edge_head_add_bwd");
+}
+
 // ---------------------------------------------------------------- 2x2 parity interleave
 // parts: 4 buffers [B*Hh*Wh, C] (order (py, px) = (0,0), (0,1), (1,0), (1,1)); out [B*(2Hh)*(2Wh), out_ld]
 __global__ void __launch_bounds__(256) interleave2x2_kernel(const __half* __restrict__ p00, const __half* __restrict__ p01,

@@ -24,7 +24,7 @@ static constexpr int WG_STAGES = 6;
 MF_DEVINL constexpr uint32_t wg_layout(int width) { return width == 64 ? 2u : (width == 32 ? 4u : 6u); }
 
 struct WgradParams {
-  int B, H, W, Cin, Ho, Wo, Cout, k, stride, pad;
+  int B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad_h, pad_w;
   int nslots;            // taps * Cin / AW
   int ntm, ntn;          // M tiles (slot pairs), N tiles
   int nkb;               // ceil(B*Ho*Wo / 64)
@@ -101,9 +101,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + NB * B_BOX);
 #pragma unroll
           for (int h = 0; h < SPT; ++h) {
-            const int ky = s_tap[h] / p.k, kx = s_tap[h] - ky * p.k;
+            const int ky = s_tap[h] / p.kw, kx = s_tap[h] - ky * p.kw;
             tma_load_im2col_4d(smem_u32(a_smem + stage * A_STAGE + h * A_BOX), &tmap_x, &full_bar[stage], s_c0[h],
-                               ox * p.stride - p.pad, oy * p.stride - p.pad, n, static_cast<uint16_t>(kx),
+                               ox * p.stride - p.pad_w, oy * p.stride - p.pad_h, n, static_cast<uint16_t>(kx),
                                static_cast<uint16_t>(ky));
           }
 #pragma unroll
@@ -144,7 +144,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   } else {
     // ================================================================ epilogue: TMEM -> fp32 atomics into OIHW dW
     const int row = warp * 32 + lane;                              // M index inside the tile
-    const int taps = p.k * p.k;
+    const int taps = p.kh * p.kw;
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       int mt, nt, kb_lo, kb_hi;
@@ -214,31 +214,31 @@ static int launch_wgrad_n(int bn, const CUtensorMap& tx, const CUtensorMap& tdy,
   return launch_wgrad_cfg<16, AW, 16>(tx, tdy, p, grid, st);
 }
 
-// x: [B*H*W, x_ld] fp16 NHWC rows; dy: [B*Ho*Wo, dy_ld] fp16 rows; dw: [Cout, Cin, k, k] fp32 (overwritten)
-int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, const __half* dy, int dy_ld, int Cout, int k,
-                      int stride, int pad, float* dw, cudaStream_t st) {
+// x: [B*H*W, x_ld] fp16 NHWC rows; dy: [B*Ho*Wo, dy_ld] fp16 rows; dw: [Cout, Cin, kh, kw] fp32 (overwritten)
+int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, const __half* dy, int dy_ld, int Cout, int kh,
+                      int kw, int stride, int pad_h, int pad_w, float* dw, cudaStream_t st) {
   static PFN_encTiledW enc = reinterpret_cast<PFN_encTiledW>(wg_driver_fn("cuTensorMapEncodeTiled"));
   static PFN_encIm2colW enc2 = reinterpret_cast<PFN_encIm2colW>(wg_driver_fn("cuTensorMapEncodeIm2col"));
   if (!enc || !enc2) { set_error("conv wgrad: tensor-map driver entry points unavailable"); return -1; }
   const bool cin_ok = Cin == 16 || Cin == 32 || (Cin > 0 && Cin % 64 == 0);
   const bool cout_ok = Cout == 16 || Cout == 32 || (Cout > 0 && Cout % 64 == 0);
-  if (!cin_ok || !cout_ok || x_ld % 8 != 0 || dy_ld % 8 != 0 || k < 1 || k > 7 || stride < 1 || stride > 8 ||
+  if (!cin_ok || !cout_ok || x_ld % 8 != 0 || dy_ld % 8 != 0 || kh < 1 || kh > 7 || kw < 1 || kw > 7 || stride < 1 || stride > 8 ||
       (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) {
-    set_error("conv wgrad: needs Cin, Cout in {16, 32, multiples of 64} and 16-byte aligned rows (Cin=%d Cout=%d k=%d s=%d)", Cin,
-              Cout, k, stride);
+    set_error("conv wgrad: needs Cin, Cout in {16, 32, multiples of 64} and 16-byte aligned rows (Cin=%d Cout=%d k=%dx%d s=%d)", Cin,
+              Cout, kh, kw, stride);
     return -1;
   }
   const int aw = Cin < 64 ? Cin : 64, bw = Cout < 64 ? Cout : 64;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
-  p.Ho = (H + 2 * pad - k) / stride + 1;
-  p.Wo = (W + 2 * pad - k) / stride + 1;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
+  p.Ho = (H + 2 * pad_h - kh) / stride + 1;
+  p.Wo = (W + 2 * pad_w - kw) / stride + 1;
   if (p.Ho < 1 || p.Wo < 1) { set_error("conv wgrad: empty output"); return -1; }
   const long long Mout = static_cast<long long>(B) * p.Ho * p.Wo;
   const int bn = Cout < 64 ? Cout : (Cout % 128 == 0 ? 128 : 64);
   const int spt = 128 / aw;
-  p.nslots = k * k * (Cin / aw);
+  p.nslots = kh * kw * (Cin / aw);
   p.ntm = (p.nslots + spt - 1) / spt;
   p.ntn = Cout / bn;
   p.nkb = static_cast<int>((Mout + WG_BK - 1) / WG_BK);
@@ -255,7 +255,7 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
   {
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(x_ld) * 2, static_cast<cuuint64_t>(x_ld) * 2 * W, static_cast<cuuint64_t>(x_ld) * 2 * W * H};
-    int lower[2] = {-pad, -pad}, upper[2] = {pad - (k - 1), pad - (k - 1)};
+    int lower[2] = {-pad_w, -pad_h}, upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
     cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
     const CUtensorMapSwizzle swa = aw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : aw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     if (enc2(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(x), gdim, gstr, lower, upper, static_cast<cuuint32_t>(aw),
@@ -274,7 +274,7 @@ int launch_conv_wgrad(const __half* x, int x_ld, int B, int H, int W, int Cin, c
       return -1;
     }
   }
-  if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * Cout * Cin * k * k, st), "conv wgrad memset")) return -1;
+  if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * Cout * Cin * kh * kw, st), "conv wgrad memset")) return -1;
   const int nitems = tiles * splits;
   const int grid = nitems < nsm ? nitems : nsm;
   if (aw == 64) return launch_wgrad_n<64>(bn, tx, tdy, p, grid, st);

@@ -444,3 +444,49 @@ def test_dcn_backward_tensor_core_path(case):
     assert rel(dom[:, :18], leaves[3].grad) < 1e-2
     assert rel(dom[:, 18:27], leaves[4].grad) < 1e-2
     assert dom[:, 27:].abs().sum().item() == 0
+
+
+def test_edge_fusion_conv1d_and_head_backward():
+    """Backward of the edge-fusion tail (detector_predictor.py:149-158): the Conv1d(256, 256, 3) weight gradient through the
+    rectangular (1 x 3) wgrad, and edge_head_add (1x1 Conv1d + indexed add) vs torch autograd on CPU."""
+    from monoflex_b200._lib import call, stream
+    from monoflex_b200 import synthetic as syn
+    import torch.nn.functional as F
+    gen = np.random.Generator(np.random.PCG64(94))
+    t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    B, K, H, W = 2, 832, 96, 320
+    # ---- Conv1d(256 -> 256, k = 3) on the replicate-padded [B, K + 2, 256] rows == 1 x 3 convolution, pad 0
+    xin = t32(gen.standard_normal((B, 256, K + 2))).half().float()
+    dy = t32(gen.standard_normal((B, 256, K)) * 0.1).half().float()
+    ref = torch.nn.grad.conv1d_weight(xin, (256, 256, 3), dy)
+    xr = xin.permute(0, 2, 1).reshape(-1, 256).contiguous().half().cuda()
+    dyr = dy.permute(0, 2, 1).reshape(-1, 256).contiguous().half().cuda()
+    dw = torch.empty(256, 256, 1, 3, dtype=torch.float32, device="cuda")
+    call("mf_conv2d_wgrad_rect_nhwc_f16", xr.data_ptr(), 256, B, 1, K + 2, 256, dyr.data_ptr(), 256, 256, 1, 3, 1, 0, 0,
+         dw.data_ptr(), stream())
+    assert (dw.cpu().view(256, 256, 3) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    # ---- edge_head_add backward
+    idx, n, _ = syn.edge_indices()
+    edge = idx.unsqueeze(0).repeat(B, 1, 1)
+    elen = torch.tensor([n, n - 37], dtype=torch.long)
+    n_out, ctot, ch0 = 2, 50, 4
+    tt = t32(gen.standard_normal((B, K, 256))).half().float().requires_grad_(True)
+    w = t32(gen.standard_normal((n_out, 256)) * 0.1).requires_grad_(True)
+    bias = t32(gen.standard_normal(n_out)).requires_grad_(True)
+    d_out = t32(gen.standard_normal((B, ctot, H, W)))
+    out = torch.zeros(B, ctot, H, W)
+    for b in range(B):                                           # the reference's python loop, detector_predictor.py:155-158
+        L = int(elen[b])
+        val = F.conv1d(tt[b].t().unsqueeze(0), w.unsqueeze(-1), bias)[0]           # [n_out, K]
+        ex, ey = edge[b, :L, 0], edge[b, :L, 1]
+        out[b, ch0:ch0 + n_out, ey, ex] = out[b, ch0:ch0 + n_out, ey, ex] + val[:, :L]
+    out.backward(d_out)
+    d_t = torch.empty(B, K, 256, dtype=torch.half, device="cuda")
+    gw = torch.empty(n_out, 256, device="cuda")
+    gb = torch.empty(n_out, device="cuda")
+    th, wc, ec, lc, dc = tt.detach().half().cuda(), w.detach().cuda(), edge.cuda(), elen.cuda(), d_out.cuda()
+    call("mf_edge_head_add_bwd", th.data_ptr(), wc.data_ptr(), n_out, ec.data_ptr(), lc.data_ptr(), dc.data_ptr(), ctot, ch0,
+         d_t.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, K, H, W, stream())
+    assert (d_t.float().cpu() - tt.grad).abs().max().item() <= 2e-3 * tt.grad.abs().max().item()
+    assert (gw.cpu() - w.grad).abs().max().item() <= 1e-4 * w.grad.abs().max().item()
+    assert (gb.cpu() - bias.grad).abs().max().item() <= 1e-4 * bias.grad.abs().max().item()
