@@ -36,11 +36,29 @@ def key2channel(key):
 
 
 # ------------------------------------------------------------------------------------------------ layers
+_TRAIN = [False]     # train-mode switch of every normalisation layer (batch statistics), see training_mode()
+
+
+class training_mode(object):
+    """with training_mode(): ... -> BatchNorm / InPlaceABN / BatchNorm1d use batch statistics like module.train()
+    (running statistics are not updated: they do not enter the forward value or the gradients)."""
+
+    def __enter__(self):
+        self.prev = _TRAIN[0]
+        _TRAIN[0] = True
+
+    def __exit__(self, *a):
+        _TRAIN[0] = self.prev
+
+
 def bn_eval(sd, p, x, abs_weight=False):
-    """nn.BatchNorm2d eval (dla_dcn.py:76 etc.): (x-mean)/sqrt(var+eps)*w+b. IABN uses |w|+eps."""
+    """nn.BatchNorm2d (dla_dcn.py:76 etc.): (x-mean)/sqrt(var+eps)*w+b, running statistics in eval mode, batch statistics
+    under training_mode(). IABN uses |w|+eps."""
     w = sd[p + '.weight']
     if abs_weight:
         w = w.abs() + BN_EPS
+    if _TRAIN[0]:
+        return F.batch_norm(x, None, None, w, sd[p + '.bias'], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], w, sd[p + '.bias'], False, 0.0, BN_EPS)
 
 
@@ -217,8 +235,11 @@ def predictor(sd, features, edge_indices, edge_lens, p='heads.predictor', out_w=
 
                 def trunc(q, e):
                     e = F.conv1d(F.pad(e, (1, 1), mode='replicate'), sd[q + '.0.weight'], sd[q + '.0.bias'])
-                    e = F.batch_norm(e, sd[q + '.1.running_mean'], sd[q + '.1.running_var'], sd[q + '.1.weight'],
-                                     sd[q + '.1.bias'], False, 0.0, BN_EPS)
+                    if _TRAIN[0]:
+                        e = F.batch_norm(e, None, None, sd[q + '.1.weight'], sd[q + '.1.bias'], True, 0.0, BN_EPS)
+                    else:
+                        e = F.batch_norm(e, sd[q + '.1.running_mean'], sd[q + '.1.running_var'], sd[q + '.1.weight'],
+                                         sd[q + '.1.bias'], False, 0.0, BN_EPS)
                     return F.conv1d(e, sd[q + '.3.weight'], sd[q + '.3.bias'])
 
                 e_cls = trunc(p + '.trunc_heatmap_conv', ef[:, :256])
@@ -543,3 +564,13 @@ def loss_computation(pred_cls, pred_reg, fields, calibs_P, down_ratio=4):
     log['soft_MAE'] = ((soft - t_depth).abs() / t_depth).mean()
     log['mean_MAE'] = ((depths.mean(1) - t_depth).abs() / t_depth).mean()
     return out, {k: v.detach() for k, v in log.items()}
+
+
+def detector_train_losses(sd, images, fields, edge_indices, edge_lens, calibs_P):
+    """KeypointDetector.forward training branch (model/detector.py:32-34 -> Detect_Head.forward detector_head.py:17-21):
+    train-mode backbone + predictor, then Loss_Computation. Returns (loss_dict, log_dict); differentiable w.r.t. every
+    tensor of `sd` that requires grad."""
+    with training_mode():
+        feats = backbone(sd, images)
+        pred = predictor(sd, feats, edge_indices, edge_lens)
+    return loss_computation(pred['cls'], pred['reg'], fields, calibs_P)

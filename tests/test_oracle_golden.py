@@ -144,3 +144,34 @@ def test_loss_oracle_matches_reference_loss_computation():
     assert abs(np.abs(g).sum() - gold["grad_reg_abs_sum"]) <= 1e-5 * gold["grad_reg_abs_sum"]
     gc = cls.grad.numpy().reshape(-1)
     assert np.abs(gc[::97] - gold["grad_cls_sample"]).max() <= 1e-5 * np.abs(gold["grad_cls_sample"]).max()
+
+
+def test_train_step_oracle_matches_reference_train_mode():
+    """oracle.detector_train_losses (train-mode BN / IABN, predictor with edge fusion, 11-term loss) + autograd vs the UNMODIFIED
+    reference model in train() mode (oracle/make_golden_train.py): losses, every parameter's gradient norm, three gradients in
+    full. This pins the oracle for the training rows (R2-R6, R11-R12 backward)."""
+    import torch
+    from monoflex_b200 import synthetic as syn
+    gold = np.load(os.path.join(GOLDEN, "train_step_2x384x1280.npz"))
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v)
+          for k, v in syn.make_state_dict(seed=0).items()}
+    fields = syn.make_train_targets(2, empty_image=0)
+    images = syn.make_images(2, 384, 1280, seed=1)
+    idx, n, _ = syn.edge_indices()
+    loss, _ = mo.detector_train_losses(sd, images, fields, idx.unsqueeze(0).repeat(2, 1, 1), torch.tensor([n, n]),
+                                       [syn.KITTI_P2] * 2)
+    for k, v in loss.items():
+        assert abs(v.item() - gold["loss_" + k]) <= 2e-4 * max(1.0, abs(gold["loss_" + k])), (k, v.item(), gold["loss_" + k])
+    sum(loss.values()).backward()
+    names, norms = list(gold["grad_names"]), gold["grad_norms"]
+    checked = 0
+    for k, ref in zip(names, norms):
+        g = sd[k].grad
+        got = 0.0 if g is None else float(g.double().norm())
+        assert abs(got - ref) <= 2e-3 * ref + 2e-5, (k, got, ref)      # conv biases in front of a train-mode BN have ~0 (noise) gradients
+        checked += ref > 0
+    assert checked >= 260
+    for k in ("backbone.base.base_layer.0.weight", "backbone.base.level2.tree1.bn1.weight", "heads.predictor.class_head.2.bias"):
+        ref = gold["grad_" + k]
+        assert np.abs(sd[k].grad.numpy() - ref).max() <= 2e-3 * np.abs(ref).max(), k
