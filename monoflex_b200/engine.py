@@ -50,8 +50,14 @@ class Act(object):
 
 
 class Plan(object):
-    def __init__(self, device):
+    def __init__(self, device, train=False):
+        """train=True: every conv/DCN followed by a normalisation layer is emitted as a raw convolution + the training-mode
+        BatchNorm kernels (batch statistics, running-stat update, fused residual + activation; csrc/mf_bn_train.cu) instead
+        of folding eval statistics into the GEMM epilogue. `bn_saved` lists (module, raw, y, stats) per layer for a backward
+        tape. Forward only so far ("Training tape")."""
         self.device = device
+        self.train = train
+        self.bn_saved = []
         self.acts = []
         self.groups = []     # (total_C, [acts]) concat groups
         self.ops = []        # (name, fn_name, argbuilder) resolved at finalize
@@ -155,9 +161,37 @@ class Plan(object):
         return scale, shift
 
     # ---- op emitters
+    def bn_train(self, raw, y, slices, act, residual=None, abs_weight=False):
+        """Emit mf_bn_train_forward for `slices` = [(module, first channel, channels)] of raw -> y (<= 256 channels per
+        launch: statistics are per channel, so column slices of one [M, ld] buffer are independent)."""
+        lib = _lib.load()
+        for mod, c_first, c_num in slices:
+            for off in range(0, c_num, 256):
+                cc = min(256, c_num - off)
+                c0 = c_first + off
+                stats = torch.empty(4, cc, dtype=torch.float32, device=self.device)
+                ws = torch.empty(max(1, lib.mf_bn_train_workspace(raw.M, cc) // 4), dtype=torch.float32, device=self.device)
+                self.keep.extend([stats, ws])
+                self.bn_saved.append((mod, raw, y, stats, c0, cc))
+                momentum = getattr(mod, "momentum", 0.1)
+                eps = getattr(mod, "eps", BN_EPS)
+                self.add("mf_bn_train_forward", lambda mod=mod, off=off, c0=c0, cc=cc, stats=stats, ws=ws, momentum=momentum, eps=eps: (
+                    raw.ptr() + 2 * c0, raw.ld, raw.M, cc, mod.weight.data_ptr() + 4 * off, mod.bias.data_ptr() + 4 * off, eps,
+                    momentum, 1 if abs_weight else 0, mod.running_mean.data_ptr() + 4 * off, mod.running_var.data_ptr() + 4 * off,
+                    (residual.ptr() + 2 * c0) if residual is not None else None, residual.ld if residual is not None else 0, act,
+                    y.ptr() + 2 * c0, y.ld, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                    ws.data_ptr()))
+
     def conv(self, x, weight, stride, pad, bn=None, bias=None, act=ACT_RELU, residual=None, out=None, abs_weight=False,
              cin_pad=None):
         cout, _, kh, kw = weight.shape if weight.dim() == 4 else (weight.shape[0], weight.shape[1], 1, weight.shape[2])
+        if self.train and bn is not None:
+            # training mode: raw convolution (+ bias), then batch-statistics normalisation + residual + activation
+            assert not isinstance(pad, tuple), "non-square padding is not built"
+            raw = self.conv(x, weight, stride, pad, None, bias, ACT_NONE, None, None, False, cin_pad)
+            y = out if out is not None else self.act(raw.B, raw.H, raw.W, cout)
+            self.bn_train(raw, y, bn if isinstance(bn, list) else [(bn, 0, cout)], act, residual, abs_weight)
+            return y
         wp, n_pad, k_pad = self.pack_weight(weight, cin_pad)
         scale, shift = self.affine(cout, n_pad, bn, bias, abs_weight)
         Ho = (x.H + 2 * pad[0] - kh) // stride + 1 if isinstance(pad, tuple) else (x.H + 2 * pad - kh) // stride + 1
@@ -190,9 +224,18 @@ class Plan(object):
                          ACT_OFFMASK, 32, stride=1, pad=1)
         cout = dcn_mod.weight.shape[0]
         wp, n_pad, k_pad = self.pack_weight(dcn_mod.weight)
+        cin = x.C
+        if self.train:
+            scale, shift = self.affine(cout, n_pad, None, dcn_mod.bias)
+            raw = self.act(x.B, x.H, x.W, cout)
+            self.add("mf_dcn_nhwc_f16", lambda: (
+                x.ptr(), x.ld, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
+                shift.data_ptr(), ACT_NONE, OUT_F16_NHWC, raw.ptr(), raw.ld))
+            y = out if out is not None else self.act(x.B, x.H, x.W, cout)
+            self.bn_train(raw, y, [(bn, 0, cout)], ACT_RELU)
+            return y
         scale, shift = self.affine(cout, n_pad, bn, dcn_mod.bias)
         y = out if out is not None else self.act(x.B, x.H, x.W, cout)
-        cin = x.C
         self.add("mf_dcn_nhwc_f16", lambda: (
             x.ptr(), x.ld, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
             shift.data_ptr(), ACT_RELU, OUT_F16_NHWC, y.ptr(), y.ld))

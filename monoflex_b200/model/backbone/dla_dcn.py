@@ -129,7 +129,7 @@ class DLA(nn.Module):
         """DLA.forward (:324-331). x8: image already packed to NHWC fp16 with 8 channels (3 real + 5 zero)."""
         import os
         rows_ok = (len(self.level0) == 3 and len(self.level1) == 3 and self.channels[0] == 16 and x8.W % 2 == 0 and
-                   self.level1[0].stride[0] == 2 and os.environ.get("MF_NO_ROWS_STEM", "0") != "1")
+                   self.level1[0].stride[0] == 2 and os.environ.get("MF_NO_ROWS_STEM", "0") != "1" and not P.train)
         y = []
         if rows_ok:
             # full-resolution stem on 16-byte-pixel planes: no im2col copies (csrc/mf_rows.cu)
@@ -238,7 +238,7 @@ class DLASeg(nn.Module):
 
     # ---- plan construction / execution
     def build_plan(self, B, H, W, device):
-        P = engine.Plan(device)
+        P = engine.Plan(device, train=self.training)
         x8 = P.act(B, H, W, 8)
         levels = self.base.plan(P, x8)
         ups = self.dla_up.plan(P, levels)
@@ -263,6 +263,18 @@ class DLASeg(nn.Module):
         if self.training:
             raise NotImplementedError("monoflex_b200 round 1 builds the inference path; the fused training path "
                                       "(SURVEY §8 rows R5/R11-R13) is not built yet - there is no PyTorch fallback")
+        if not x.is_cuda:
+            raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only (input is on %s); no CPU fallback" % x.device)
+        x = x.float().contiguous()
+        plan = self._plan_for(x)
+        self.run_plan(plan, x)
+        return plan.output.nchw_view()
+
+    def train_forward(self, x):
+        """Train-mode forward of the backbone (batch-statistics BatchNorm, running statistics updated in place) on the
+        CUDA kernels. Forward only: the backward tape is not built yet, so this is NOT reachable through forward()."""
+        if not self.training:
+            raise RuntimeError("train_forward needs module.train()")
         if not x.is_cuda:
             raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only (input is on %s); no CPU fallback" % x.device)
         x = x.float().contiguous()

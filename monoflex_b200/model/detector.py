@@ -38,6 +38,19 @@ class KeypointDetector(nn.Module):
             return self.heads(features, targets, test=self.test)
         return self._forward_graph(x, targets)
 
+    def train_forward_losses(self, images, targets):
+        """Train-mode FORWARD of the whole detector on the CUDA kernels: backbone and predictor with batch-statistics
+        normalisation (running statistics are updated), then Loss_Computation -> (loss_dict, log_loss_dict) like the
+        reference's training branch (model/detector.py:32-34). The losses are differentiable w.r.t. the head outputs only:
+        the layer-by-layer backward tape is not built yet, which is why forward() still raises in training mode instead of
+        returning losses whose backward() would silently stop at the predictor."""
+        if not self.training:
+            raise RuntimeError("train_forward_losses needs model.train()")
+        x = to_image_list(images).tensors
+        features = self.backbone.train_forward(x)
+        pred = self.heads.predictor.train_forward(features, targets)
+        return self.heads.loss_evaluator(pred, targets)
+
     def forward_async(self, images, targets):
         """Enqueue one eval forward (graph replay) and return a handle; `handle.result()` waits for it and returns what
         `forward` returns. Lets a caller overlap the host-side read of step i with the GPU work of step i+1 (the decode

@@ -76,7 +76,7 @@ class _predictor(nn.Module):
     def build_plan(self, feat, K_edge):
         """feat: engine.Act-like description of the [B,H,W,64] fp16 feature rows."""
         dev = feat.buf.device
-        P = engine.Plan(dev)
+        P = engine.Plan(dev, train=self.training)
         B, H, W, hc = feat.B, feat.H, feat.W, self.head_conv
         x = P.act(B, H, W, feat.C)
         x.buf, x.ch_off, x.owner = feat.buf, feat.ch_off, None
@@ -103,7 +103,7 @@ class _predictor(nn.Module):
             off_ch0 = ch0s[self.offset_index[0]] + sum(h.weight.shape[0] for h in
                                                        list(self.reg_heads[self.offset_index[0]])[:self.offset_index[1]])
         import os
-        fused = os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
+        fused = not P.train and os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
             all(sum(h.weight.shape[0] for h in heads) <= 32 for heads in self.reg_heads) and self.num_classes <= 32
         if fused:
             # ---- one kernel: 9 x (3x3 conv + IABN) + every 1x1 head; hidden activations stay on chip (csrc/mf_head.cu)
@@ -157,7 +157,9 @@ class _predictor(nn.Module):
             hid.ld = hid_ld
             edge_cols = (0, hc)
         else:
-            hid = P.conv(x, w_all, 1, 1, abn, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
+            # train mode: every branch normalises with its own InPlaceABN module (batch statistics, running-stat update)
+            norm = [(b[1], i * hc, hc) for i, b in enumerate(branches)] if P.train else abn
+            hid = P.conv(x, w_all, 1, 1, norm, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
 
             def slice_of(i):
                 sl = P.act(B, H, W, hc)
@@ -218,6 +220,15 @@ class _predictor(nn.Module):
     def forward(self, features, targets):
         if self.training:
             raise NotImplementedError("training path not built yet (no PyTorch fallback)")
+        return self._run(features, targets)
+
+    def train_forward(self, features, targets):
+        """Train-mode forward (InPlaceABN / BatchNorm1d on batch statistics). Forward only, see DLASeg.train_forward."""
+        if not self.training:
+            raise RuntimeError("train_forward needs module.train()")
+        return self._run(features, targets)
+
+    def _run(self, features, targets):
         plan = self.plan_for(features, targets[0].get_field("edge_indices").shape[0])
         self.load_targets(plan, targets)
         plan.run()

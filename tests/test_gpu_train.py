@@ -490,3 +490,32 @@ def test_edge_fusion_conv1d_and_head_backward():
     assert (d_t.float().cpu() - tt.grad).abs().max().item() <= 2e-3 * tt.grad.abs().max().item()
     assert (gw.cpu() - w.grad).abs().max().item() <= 1e-4 * w.grad.abs().max().item()
     assert (gb.cpu() - bias.grad).abs().max().item() <= 1e-4 * bias.grad.abs().max().item()
+
+
+def test_train_mode_forward_losses_vs_reference_golden():
+    """Train-mode FORWARD of the whole detector on the CUDA kernels (batch-statistics BN / IABN / BN1d, unfused head, 11-term
+    loss) against the losses of the UNMODIFIED reference in train() mode (tests/golden/train_step_2x384x1280.npz). fp16
+    operands end to end, so the comparison is at the few-percent level per loss term; the exact-arithmetic check of every
+    operator is in the tests above."""
+    import os
+    from conftest import GOLDEN
+    from monoflex_b200 import synthetic as syn
+    from monoflex_b200.model.detector import KeypointDetector
+    gold = np.load(os.path.join(GOLDEN, "train_step_2x384x1280.npz"))
+    model = KeypointDetector(default_cfg()).cuda()
+    model.load_state_dict(syn.make_state_dict(seed=0), strict=False)
+    model.train()
+    fields = syn.make_train_targets(2, empty_image=0)
+    images = syn.make_images(2, 384, 1280, seed=1).cuda()
+    targets = [t.to("cuda") for t in syn.make_train_param_lists(fields)]
+    rm_before = model.backbone.base.level2.tree1.bn1.running_mean.clone()
+    loss_dict, log = model.train_forward_losses(images, targets)
+    torch.cuda.synchronize()
+    assert list(loss_dict) == mo.LOSS_NAMES
+    for k in mo.LOSS_NAMES:
+        ref = float(gold["loss_" + k])
+        got = loss_dict[k].item()
+        assert np.isfinite(got) and abs(got - ref) <= 5e-2 * max(abs(ref), 0.05), (k, got, ref)
+    assert not torch.equal(model.backbone.base.level2.tree1.bn1.running_mean, rm_before)      # running statistics moved
+    with pytest.raises(NotImplementedError):
+        model(images, targets)                                                                # forward() still refuses to train
