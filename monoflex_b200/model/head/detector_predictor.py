@@ -198,6 +198,10 @@ class _predictor(nn.Module):
         P.add("mf_sigmoid_clamp", lambda: (cls.data_ptr(), n_cls))
         P.finalize()
         P.cls, P.reg, P.hidden = cls, reg, hid
+        if P.train:       # what head_backward.predictor_backward needs: activations kept by the train-mode forward
+            P.ctx = dict(x=x, hid=hid, ea=ea if self.enable_edge_fusion else None, eb=eb if self.enable_edge_fusion else None,
+                         bn={id(m): (raw, y, st, c0, cc) for (m, raw, y, st, c0, cc) in P.bn_saved}, K_edge=K_edge,
+                         off_ch0=off_ch0, ch0s=ch0s)
         return P
 
     def plan_for(self, features, K_edge):

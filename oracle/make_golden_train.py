@@ -36,7 +36,14 @@ def main(batch=2):
     for t in targets:
         t.add_field("edge_indices", idx)
         t.add_field("edge_len", torch.tensor(n, dtype=torch.long))
+    feats = {}
+
+    def keep(_m, _inp, out):                       # gradient w.r.t. the backbone's output feature map (head-backward check)
+        out.retain_grad()
+        feats["f"] = out
+    hook = model.backbone.register_forward_hook(keep)
     loss_dict, log = model(images, targets)
+    hook.remove()
     total = sum(v for v in loss_dict.values())
     total.backward()
     out = {"loss_" + k: np.float32(v.item()) for k, v in loss_dict.items()}
@@ -45,6 +52,9 @@ def main(batch=2):
     for k, p in model.named_parameters():
         names.append(k)
         norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    gf = feats["f"].grad
+    out["grad_features_norm"] = np.float64(gf.double().norm())
+    out["grad_features_sample"] = gf.reshape(-1)[::997].numpy().astype(np.float32)
     out["grad_names"] = np.array(names)
     out["grad_norms"] = np.array(norms, dtype=np.float64)
     for k, p in model.named_parameters():
