@@ -155,6 +155,8 @@ int mf_edge_gather_bwd(const void* d_ea, const void* d_eb, int ch_a, int ch_b, c
 int mf_edge_head_add_bwd(const void* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
                          const float* d_out, int out_ctot, int out_ch0, void* d_t, float* dw, float* dbias, int B, int K, int H,
                          int W, void* stream);
+/* dst[r, 0:C] += src[r, 0:C] on fp16 rows (gradient accumulation of activations with several consumers) */
+int mf_add_rows_f16(void* dst, int dst_ld, const void* src, int src_ld, long long M, int C, void* stream);
 int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
                               int B, int Hh, int Wh, int C, void* stream);
 

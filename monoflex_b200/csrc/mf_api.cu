@@ -221,6 +221,9 @@ int mf_edge_head_add_bwd(const void* t, const float* w, int n_out, const long lo
   return launch_edge_head_add_bwd(static_cast<const __half*>(t), w, n_out, edge_idx, edge_len, d_out, out_ctot, out_ch0,
                                   static_cast<__half*>(d_t), dw, dbias, B, K, H, W, MF_STREAM(stream));
 }
+int mf_add_rows_f16(void* dst, int dst_ld, const void* src, int src_ld, long long M, int C, void* stream) {
+  return launch_add_rows(static_cast<__half*>(dst), dst_ld, static_cast<const __half*>(src), src_ld, M, C, MF_STREAM(stream));
+}
 int mf_interleave2x2_nhwc_f16(const void* p00, const void* p01, const void* p10, const void* p11, int part_ld, void* out, int out_ld,
                               int B, int Hh, int Wh, int C, void* stream) {
   return launch_interleave2x2(static_cast<const __half*>(p00), static_cast<const __half*>(p01), static_cast<const __half*>(p10),

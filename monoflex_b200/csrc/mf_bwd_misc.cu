@@ -337,6 +337,29 @@ int launch_edge_head_add_bwd(const __half* t, const float* w, int n_out, const l
   return check_cuda(cudaGetLastError(), "edge_head_add_bwd");
 }
 
+// ---------------------------------------------------------------- dst[r, 0:C] += src[r, 0:C] (gradient accumulation)
+__global__ void __launch_bounds__(256) add_rows_kernel(__half* __restrict__ dst, int dst_ld, const __half* __restrict__ src,
+                                                       int src_ld, long long M, int C) {
+  pdl_wait();
+  const int CV = C / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * CV) return;
+  const int cv = static_cast<int>(i % CV);
+  const long long row = i / CV;
+  float a[8], b[8];
+  bm_unpack8(*reinterpret_cast<const uint4*>(dst + row * dst_ld + cv * 8), a);
+  bm_unpack8(__ldg(reinterpret_cast<const uint4*>(src + row * src_ld + cv * 8)), b);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] += b[e];
+  *reinterpret_cast<uint4*>(dst + row * dst_ld + cv * 8) = bm_pack8(a);
+}
+int launch_add_rows(__half* dst, int dst_ld, const __half* src, int src_ld, long long M, int C, cudaStream_t st) {
+  if (C % 8 || dst_ld % 8 || src_ld % 8) { set_error("add_rows: bad shape"); return -1; }
+  const long long n = M * (C / 8);
+  (void)launch_k(add_rows_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, dst, dst_ld, src, src_ld, M, C);
+  return check_cuda(cudaGetLastError(), "add_rows");
+}
+
 // ---------------------------------------------------------------- 2x2 parity interleave
 // parts: 4 buffers [B*Hh*Wh, C] (order (py, px) = (0,0), (0,1), (1,0), (1,1)); out [B*(2Hh)*(2Wh), out_ld]
 __global__ void __launch_bounds__(256) interleave2x2_kernel(const __half* __restrict__ p00, const __half* __restrict__ p01,

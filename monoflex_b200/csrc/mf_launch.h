@@ -41,6 +41,7 @@ int launch_edge_gather_bwd(const __half* d_ea, const __half* d_eb, int ch_a, int
 int launch_edge_head_add_bwd(const __half* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
                              const float* d_out, int out_ctot, int out_ch0, __half* d_t, float* dw, float* dbias, int B, int K,
                              int H, int W, cudaStream_t st);
+int launch_add_rows(__half* dst, int dst_ld, const __half* src, int src_ld, long long M, int C, cudaStream_t st);
 int launch_interleave2x2(const __half* p00, const __half* p01, const __half* p10, const __half* p11, int part_ld, __half* out,
                          int out_ld, int B, int Hh, int Wh, int C, cudaStream_t st);
 int launch_dcn_sample_cols(const __half* x, int x_ld, const float* om, int om_ld, __half* cols, int B, int H, int W, int C,

@@ -58,6 +58,7 @@ class Plan(object):
         self.device = device
         self.train = train
         self.bn_saved = []
+        self.tape = []       # train mode: one record per emitted layer, consumed in reverse by monoflex_b200/tape.py
         self.acts = []
         self.groups = []     # (total_C, [acts]) concat groups
         self.ops = []        # (name, fn_name, argbuilder) resolved at finalize
@@ -190,7 +191,11 @@ class Plan(object):
             assert not isinstance(pad, tuple), "non-square padding is not built"
             raw = self.conv(x, weight, stride, pad, None, bias, ACT_NONE, None, None, False, cin_pad)
             y = out if out is not None else self.act(raw.B, raw.H, raw.W, cout)
-            self.bn_train(raw, y, bn if isinstance(bn, list) else [(bn, 0, cout)], act, residual, abs_weight)
+            slices = bn if isinstance(bn, list) else [(bn, 0, cout)]
+            first = len(self.bn_saved)
+            self.bn_train(raw, y, slices, act, residual, abs_weight)
+            self.tape.append(dict(kind="conv_bn", x=x, weight=weight, bias=bias, stride=stride, pad=pad, raw=raw, y=y, act=act,
+                                  residual=residual, abs_weight=abs_weight, bn=self.bn_saved[first:]))
             return y
         wp, n_pad, k_pad = self.pack_weight(weight, cin_pad)
         scale, shift = self.affine(cout, n_pad, bn, bias, abs_weight)
@@ -232,7 +237,9 @@ class Plan(object):
                 x.ptr(), x.ld, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
                 shift.data_ptr(), ACT_NONE, OUT_F16_NHWC, raw.ptr(), raw.ld))
             y = out if out is not None else self.act(x.B, x.H, x.W, cout)
+            first = len(self.bn_saved)
             self.bn_train(raw, y, [(bn, 0, cout)], ACT_RELU)
+            self.tape.append(dict(kind="dcn", x=x, mod=dcn_mod, om=om, raw=raw, y=y, bn=self.bn_saved[first:]))
             return y
         scale, shift = self.affine(cout, n_pad, bn, dcn_mod.bias)
         y = out if out is not None else self.act(x.B, x.H, x.W, cout)
@@ -267,6 +274,8 @@ class Plan(object):
     def maxpool2(self, x, out=None):
         y = out if out is not None else self.act(x.B, x.H // 2, x.W // 2, x.C)
         self.add("mf_maxpool2_nhwc_f16", lambda: (x.ptr(), y.ptr(), x.B, x.H, x.W, x.C, x.ld, y.ld))
+        if self.train:
+            self.tape.append(dict(kind="maxpool2", x=x, y=y))
         return y
 
     def upsample_add(self, x, up_weight, skip, f):
@@ -279,6 +288,8 @@ class Plan(object):
         self.add("mf_upsample_add_nhwc_f16", lambda: (
             x.ptr(), wt.data_ptr(), skip.ptr() if skip is not None else None, y.ptr(), x.B, x.H, x.W, C, f, x.ld,
             skip.ld if skip is not None else 0, y.ld))
+        if self.train:
+            self.tape.append(dict(kind="upsample_add", x=x, weight=up_weight, wt=wt, skip=skip, f=f, y=y))
         return y
 
 
