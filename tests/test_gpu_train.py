@@ -609,6 +609,10 @@ def test_full_backward_tape_vs_reference_gradients():
         if want < 1e-5:                                          # conv biases in front of a train-mode BN: analytically zero
             continue
         devs.append((abs(got - want) / want, name, got, want))
+    if os.environ.get("MF_TAPE_DUMP"):
+        with open(os.environ["MF_TAPE_DUMP"], "w") as fh:
+            for d, name, got, want in devs:
+                fh.write("%-60s got %.6g want %.6g dev %+.3f\n" % (name, got, want, (got - want) / want))
     devs.sort(reverse=True)
     print("worst:", devs[:5], "median dev:", devs[len(devs) // 2][0], "n:", len(devs), "missing:", missing)
     assert missing == ["base.base_layer.0.weight"]
