@@ -10,8 +10,9 @@ others through a temporary + `mf_add_rows_f16`. Accumulating everywhere makes th
 a multiply-used activation runs first. Weight gradients are fp32. Gradients travel in fp16, so the seed must carry a loss
 scale (see head_backward.py).
 
-The 7x7 stem convolution reads the 8-channel packed image; its weight gradient runs on a 16-channel zero-padded copy of the
-rows (the narrowest box the tensor-core wgrad takes).
+The 7x7 stem convolution reads the 8-channel packed image; with `stem_wgrad=True` its weight gradient runs on a 16-channel
+zero-padded copy of the rows (the narrowest box the tensor-core wgrad takes) - written but NOT yet run on hardware (the
+round's GPU budget ended), so it is opt-in and the default reports that one gradient as missing (None).
 """
 import torch
 
@@ -71,7 +72,7 @@ def _bn_backward(rec_bn, raw, y, dy_ptr, dy_ld, d_raw, d_res, act, abs_weight, p
         put(mod.bias, dg[1], off, cc)
 
 
-def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_dx=True, cout_real=None):
+def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_dx=True, stem_wgrad=False):
     """gradients of y = conv(x, weight) + bias given d_raw = dL/dy rows [B*Ho*Wo, Cout(_padded)] fp16."""
     dev = d_raw.device
     cout, cin, kh, kw = weight.shape
@@ -81,7 +82,7 @@ def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_
         call("mf_conv2d_wgrad_nhwc_f16", x.ptr(), x.ld, x.B, x.H, x.W, cin, d_raw.data_ptr(), cout_p, cout_p, kh, stride, pad,
              dw.data_ptr(), _st())
         put(weight, dw[:cout])
-    elif cin_w_real := (weight.shape[1] if x.C == 8 else 0):
+    elif cin_w_real := (weight.shape[1] if (x.C == 8 and stem_wgrad) else 0):
         # 7x7 stem on the packed image (8 channels = 3 real + 5 zero): widen the rows to the narrowest supported box (16)
         x16 = torch.zeros(x.M, 16, dtype=torch.half, device=dev)
         x16[:, :8] = x.buf.view(x.M, -1)[:, x.ch_off:x.ch_off + 8]
@@ -114,7 +115,7 @@ def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_
 
 
 @torch.no_grad()
-def backbone_backward(backbone, plan, d_feat_rows):
+def backbone_backward(backbone, plan, d_feat_rows, stem_wgrad=False):
     """backbone: DLASeg in train mode, plan: its last train-mode plan (backbone.last_plan), d_feat_rows [B*H/4*W/4, 64] fp16:
     (scaled) gradient of the loss w.r.t. the backbone's output feature map.
     Returns {parameter name: fp32 gradient or None (not built)} for every parameter the forward used."""
@@ -146,7 +147,7 @@ def backbone_backward(backbone, plan, d_feat_rows):
             if residual is not None:
                 G.add(residual, d_res)
             _conv_backward(G, x, rec["weight"], rec["bias"], rec["stride"], rec["pad"], d_raw, raw.B, raw.H, raw.W, put,
-                           need_dx=x is not plan.input)
+                           need_dx=x is not plan.input, stem_wgrad=stem_wgrad)
         elif kind == "dcn":
             x, raw, y, mod, om = rec["x"], rec["raw"], rec["y"], rec["mod"], rec["om"]
             d_raw = torch.empty(raw.M, raw.C, dtype=torch.half, device=dev)

@@ -3,6 +3,10 @@
     forward (train-mode plans) -> Loss_Computation -> head_backward + tape (all parameter gradients) -> gradient arena ->
     FusedAdamW (one launch; `step_exchange()` instead when the optimiser was built with a symmetric group).
 
+STATUS: written at the end of round 1 and NOT yet executed on hardware (the GPU budget was exhausted; every piece it calls
+is hardware-verified on its own: train-mode forward, loss, head + backbone backward tape, FusedAdamW) - its test
+(tests/test_gpu_train.py::test_end_to_end_train_steps) therefore only runs with MF_RUN_UNVERIFIED=1.
+
 This wiring is eager Python over freshly rebuilt plans (the optimiser step changes the weights, the cached plans key on the
 parameter versions, so every step re-packs the weights and re-allocates the activation buffers): it establishes CORRECTNESS
 of the whole step, not its speed - see DESIGN.md "Training tape" for the static-plan / CUDA-graph version it is a stepping
@@ -42,7 +46,7 @@ class Trainer(object):
         loss_dict, log = model.heads.loss_evaluator({"cls": c, "reg": r}, targets)
         (S * sum(loss_dict.values())).backward()                              # fused loss backward -> d cls, d reg
         hgrads, d_feat = predictor_backward(pred_mod, pred_mod.last_plan, c.grad, r.grad)
-        bgrads = backbone_backward(model.backbone, model.backbone.last_plan, d_feat)
+        bgrads = backbone_backward(model.backbone, model.backbone.last_plan, d_feat, stem_wgrad=True)
         self.optimizer.zero_grad()
         got = set()
         with torch.no_grad():

@@ -624,6 +624,8 @@ def test_full_backward_tape_vs_reference_gradients():
     assert devs[len(devs) // 2][0] < 0.06
 
 
+@pytest.mark.skipif(__import__("os").environ.get("MF_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget ended: not yet executed on hardware (set MF_RUN_UNVERIFIED=1)")
 def test_end_to_end_train_steps():
     """forward -> loss -> whole-network backward -> arena -> one-launch AdamW, two steps on one batch (monoflex_b200/train.py):
     first-step loss equals the reference's train-mode total, every parameter of the forward graph receives a gradient
