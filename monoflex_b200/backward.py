@@ -106,7 +106,6 @@ def conv2d_dgrad_stride2(dy_rows, weight, B, Ho, Wo):
     convolution splits by output parity (py, px) into four stride-1 convolutions of dY whose 3x3 kernels hold the 1, 2, 2
     or 4 taps of W that reach that parity (zeros elsewhere) - run on the forward tensor-core kernel - and a 2x2 interleave.
     dy_rows [B*Ho*Wo, Cout] fp16 -> dx_rows [B*(2Ho)*(2Wo), Cin] fp16."""
-    from ._lib import load
     dy_rows = _rows(dy_rows, "dy_rows")
     cout, cin, k, k2 = weight.shape
     if (k, k2) != (3, 3) or dy_rows.shape != (B * Ho * Wo, cout):
@@ -135,7 +134,6 @@ def conv2d_dgrad_stride2(dy_rows, weight, B, Ho, Wo):
     dx = torch.empty(B * 2 * Ho * 2 * Wo, cin, dtype=torch.half, device=dy_rows.device)
     call("mf_interleave2x2_nhwc_f16", parts[0].ptr(), parts[1].ptr(), parts[2].ptr(), parts[3].ptr(), parts[0].ld, dx.data_ptr(),
          cin, B, Ho, Wo, cin, _st())
-    load()
     return dx
 
 

@@ -82,8 +82,9 @@ def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_
         call("mf_conv2d_wgrad_nhwc_f16", x.ptr(), x.ld, x.B, x.H, x.W, cin, d_raw.data_ptr(), cout_p, cout_p, kh, stride, pad,
              dw.data_ptr(), _st())
         put(weight, dw[:cout])
-    elif cin_w_real := (weight.shape[1] if (x.C == 8 and stem_wgrad) else 0):
+    elif x.C == 8 and stem_wgrad:
         # 7x7 stem on the packed image (8 channels = 3 real + 5 zero): widen the rows to the narrowest supported box (16)
+        cin_w_real = weight.shape[1]
         x16 = torch.zeros(x.M, 16, dtype=torch.half, device=dev)
         x16[:, :8] = x.buf.view(x.M, -1)[:, x.ch_off:x.ch_off + 8]
         dw = torch.empty(cout_p, 16, kh, kw, dtype=torch.float32, device=dev)

@@ -65,8 +65,7 @@ class Trainer(object):
                     group["initial_lr"] = 0.0
             self._unused_frozen = True
         if self.optimizer._symm is not None:
-            # every rank wrote loss-scale x gradient; the exchange kernel divides by world, the extra 1/S goes through lr_scale-free
-            # path: pre-divide the arena (one launch) to keep the fused kernel's interface unchanged
+            # the fused exchange kernel scales the reduced gradient by 1/world only: remove the loss scale first (one launch)
             self.optimizer.arena.grads.mul_(1.0 / S)
             self.optimizer.step_exchange()
         else:
