@@ -67,6 +67,37 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
                        int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
                        int out_planar, int out_npar, void* y, int y_ld, void* stream);
 
+/* ---- Strict-precision ("split") operators: the reference computes in fp32 (dcn_v2_cuda.cu:58 `scalar_t = float`, cuDNN fp32
+ * convs); one fp16 tensor-core pass per layer leaves 2-4e-3 end to end, above the 1e-3 parity contract. In strict mode every
+ * activation / weight is an fp16 PAIR hi = fp16(v), lo = fp16(v - hi) (lo block `*_lo` elements after the hi block in the same
+ * NHWC row) and a GEMM accumulates A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32 (K axis tripled, weights packed by
+ * mf_pack_conv_weight_split: k' = ((tap*nchunk + chunk)*3 + which)*cw + c, cw = min(Cin, 64)).
+ * split_in: x (and w_packed) are pairs; split_out: the fp16 NHWC output and the residual are pairs (fp32 outputs are plain). */
+int mf_pack_conv_weight_split(const float* w_oihw, int Cout, int Cin, int kh, int kw, int n_pad, int k_pad, void* out_f16,
+                              void* stream);
+int mf_conv2d_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const void* w_packed, int n_pad,
+                         int k_pad, int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift,
+                         const void* res, int res_ld, int res_lo, int act, int out_mode, void* y, int y_ld, int y_lo,
+                         int split_in, int split_out, void* stream);
+/* fused DCNv2 (mf_dcn_nhwc_f16) on pairs: corners of both halves are blended in fp32 once per (pixel, tap, 8 channels) */
+int mf_dcn_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const float* offmask, int om_ld,
+                      const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
+                      void* y, int y_ld, int y_lo, void* stream);
+/* image [B,3,H,W] fp32 -> [B*H*W, 16] fp16 rows [hi3 | lo3 | hi3 | 0 x 7] (the stem then is a plain 16-channel conv with
+ * per-tap weights [W_hi | W_hi | W_lo | 0]) */
+int mf_pack_image_split(const float* x_nchw, void* y_rows16, int B, int C, int H, int W, void* stream);
+int mf_maxpool2_split(const void* x, int x_lo, void* y, int y_lo, int B, int H, int W, int C, int x_ld, int y_ld, void* stream);
+int mf_upsample_add_split(const void* x, int x_lo, const float* w_taps, const void* skip, int skip_lo, void* y, int y_lo, int B,
+                          int Hi, int Wi, int C, int f, int x_ld, int skip_ld, int y_ld, void* stream);
+/* edge fusion on pairs: ea / eb are [B, K+2, 512] rows = [hi 256 | lo 256] */
+int mf_edge_gather_split(const void* feat, int feat_ld, int feat_lo, int ch_a, int ch_b, const long long* edge_idx, void* ea,
+                         void* eb, int B, int H, int W, int K, int out_w, int out_h, void* stream);
+int mf_edge_head_add_split(const void* t, int t_ld, int t_lo, const float* w, const float* bias, int n_out,
+                           const long long* edge_idx, const long long* edge_len, float* out, int out_ctot, int out_ch0, int B,
+                           int K, int H, int W, void* stream);
+/* pair rows -> fp32 NCHW (hi + lo): feature-map export */
+int mf_split_to_nchw_f32(const void* x, int x_ld, int x_lo, float* y, int B, int C, int HW, void* stream);
+
 /* Fused predictor head (detector_predictor.py:121-135): `nbranch` shared-input 3x3 convs (Cin -> 256 each) + InPlaceABN
  * (scale/shift, leaky 0.01) + the 1x1 output convs of every branch in one persistent kernel; the 256-channel hidden
  * activations stay on chip (staged in smem as the A operand of a second tcgen05.mma) except for branches with

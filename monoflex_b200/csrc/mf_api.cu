@@ -107,6 +107,74 @@ int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, co
   return run_gemm(p, w_packed, n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
 }
 
+// strict-precision variants: operands / outputs are hi/lo fp16 pairs (mf_split.cu); K axis of a split-input GEMM = 3 x taps x Cin
+int mf_pack_conv_weight_split(const float* w_oihw, int Cout, int Cin, int kh, int kw, int n_pad, int k_pad, void* out_f16,
+                              void* stream) {
+  return launch_pack_conv_weight_split(w_oihw, Cout, Cin, kh, kw, n_pad, k_pad, static_cast<__half*>(out_f16), MF_STREAM(stream));
+}
+int mf_conv2d_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const void* w_packed, int n_pad,
+                         int k_pad, int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift,
+                         const void* res, int res_ld, int res_lo, int act, int out_mode, void* y, int y_ld, int y_lo,
+                         int split_in, int split_out, void* stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __half*>(x); p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - kh) / stride + 1;
+  p.Wo = (W + 2 * pad - kw) / stride + 1;
+  p.M = B * p.Ho * p.Wo;
+  p.split_in = split_in ? 1 : 0; p.split_out = split_out ? 1 : 0;
+  p.x_lo = x_lo; p.res_lo = res_lo; p.y_lo = y_lo;
+  p.cw = Cin < 64 ? Cin : 64;
+  p.K_real = (p.split_in ? 3 : 1) * kh * kw * Cin;
+  p.nkb = (p.K_real + 63) / 64;
+  p.Cout = Cout; p.scale = scale; p.shift = shift;
+  p.res = static_cast<const __half*>(res); p.res_ld = res_ld; p.act = act; p.out_mode = out_mode; p.y = y; p.y_ld = y_ld;
+  if (p.Ho <= 0 || p.Wo <= 0 || Cout <= 0) { set_error("mf_conv2d_nhwc_f16x2: empty output"); return -1; }
+  if (g_conv_impl == 1) { set_error("mf_conv2d_nhwc_f16x2: no CUDA-core cross-check of the split path"); return -1; }
+  return launch_igemm2(p, static_cast<const __half*>(w_packed), n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
+}
+int mf_dcn_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const float* offmask, int om_ld,
+                      const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
+                      void* y, int y_ld, int y_lo, void* stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __half*>(x); p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.kh = 3; p.kw = 3; p.stride = 1; p.pad = 1; p.Ho = H; p.Wo = W; p.M = B * H * W;
+  p.split_in = 1; p.split_out = 1; p.x_lo = x_lo; p.y_lo = y_lo; p.cw = 64;
+  p.K_real = 27 * Cin; p.nkb = (p.K_real + 63) / 64;
+  p.offmask = offmask; p.om_ld = om_ld;
+  p.Cout = Cout; p.scale = scale; p.shift = shift; p.act = act; p.out_mode = OUT_F16_NHWC; p.y = y; p.y_ld = y_ld;
+  if (om_ld < 27) { set_error("mf_dcn_nhwc_f16x2: om_ld < 27"); return -1; }
+  return launch_igemm2(p, static_cast<const __half*>(w_packed), n_pad, k_pad, MODE_DCN, MF_STREAM(stream));
+}
+int mf_pack_image_split(const float* x_nchw, void* y_rows16, int B, int C, int H, int W, void* stream) {
+  return launch_pack_image_split(x_nchw, static_cast<__half*>(y_rows16), B, C, H, W, MF_STREAM(stream));
+}
+int mf_maxpool2_split(const void* x, int x_lo, void* y, int y_lo, int B, int H, int W, int C, int x_ld, int y_ld, void* stream) {
+  return launch_maxpool2_split(static_cast<const __half*>(x), x_lo, static_cast<__half*>(y), y_lo, B, H, W, C, x_ld, y_ld,
+                               MF_STREAM(stream));
+}
+int mf_upsample_add_split(const void* x, int x_lo, const float* w_taps, const void* skip, int skip_lo, void* y, int y_lo, int B,
+                          int Hi, int Wi, int C, int f, int x_ld, int skip_ld, int y_ld, void* stream) {
+  return launch_upsample_add_split(static_cast<const __half*>(x), x_lo, w_taps, static_cast<const __half*>(skip), skip_lo,
+                                   static_cast<__half*>(y), y_lo, B, Hi, Wi, C, f, x_ld, skip_ld, y_ld, MF_STREAM(stream));
+}
+int mf_edge_gather_split(const void* feat, int feat_ld, int feat_lo, int ch_a, int ch_b, const long long* edge_idx, void* ea,
+                         void* eb, int B, int H, int W, int K, int out_w, int out_h, void* stream) {
+  return launch_edge_gather_split(static_cast<const __half*>(feat), feat_ld, feat_lo, ch_a, ch_b, edge_idx,
+                                  static_cast<__half*>(ea), static_cast<__half*>(eb), B, H, W, K, out_w, out_h, MF_STREAM(stream));
+}
+int mf_edge_head_add_split(const void* t, int t_ld, int t_lo, const float* w, const float* bias, int n_out,
+                           const long long* edge_idx, const long long* edge_len, float* out, int out_ctot, int out_ch0, int B,
+                           int K, int H, int W, void* stream) {
+  return launch_edge_head_add_split(static_cast<const __half*>(t), t_ld, t_lo, w, bias, n_out, edge_idx, edge_len, out, out_ctot,
+                                    out_ch0, B, K, H, W, MF_STREAM(stream));
+}
+int mf_split_to_nchw_f32(const void* x, int x_ld, int x_lo, float* y, int B, int C, int HW, void* stream) {
+  return launch_split_to_nchw(static_cast<const __half*>(x), x_ld, x_lo, y, B, C, HW, MF_STREAM(stream));
+}
+
 int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar, const void* w_packed, int n_pad, int k_pad,
                        int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
                        int out_planar, int out_npar, void* y, int y_ld, void* stream) {

@@ -27,15 +27,19 @@ static constexpr int A_STAGE = BM * BK * 2;   // 16 KB
 
 static constexpr int AS_MAX_KB = 9;          // A-stationary mode: at most 9 resident K blocks (3x3 taps of 64 channels)
 
-template <int BLOCK_N, int MODE>
+// SPLIT: the fp16 NHWC output is a hi/lo pair (strict-precision mode): two staging tiles per 64-channel sub-tile, paid for
+// with one pipeline stage (the K loop of a split layer is 3x longer, so the shallower ring costs nothing measurable).
+template <int BLOCK_N, int MODE, bool SPLIT = false>
 struct Cfg2 {
   static constexpr bool A_STAT = MODE == MODE_CONV_TMA_AS;
-  static constexpr int STAGES = A_STAT ? 3 : (MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : (BLOCK_N >= 32 ? 5 : 6))));
+  static constexpr int STAGES0 = A_STAT ? 3 : (MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : (BLOCK_N >= 32 ? 5 : 6))));
+  static constexpr int STAGES = (SPLIT && BLOCK_N >= 64) ? ((MODE == MODE_DCN && BLOCK_N < 128) ? STAGES0 : STAGES0 - 1) : STAGES0;
   static constexpr int A_REGION = (A_STAT ? AS_MAX_KB : STAGES) * A_STAGE;
   static constexpr int LAG = BLOCK_N >= 64 ? 3 : (BLOCK_N >= 32 ? 3 : 4);   // cp.async groups in flight per producer thread
   static constexpr int CTAS_PER_SM = BLOCK_N >= 64 ? 1 : 2;
   static constexpr int B_STAGE = BLOCK_N * BK * 2;
-  static constexpr int OUT_STAGE = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;
+  static constexpr int OUT_HALF = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;     // staging of one fp16 tile
+  static constexpr int OUT_STAGE = SPLIT ? 2 * OUT_HALF : OUT_HALF;
   static constexpr int BAR_BYTES = 256;                         // barriers + tmem ptr
   static constexpr int PRM_BYTES = MODE == MODE_DCN ? 9 * BM * 32 : 0;   // DCN sampling records
   static constexpr int SMEM = A_REGION + STAGES * B_STAGE + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + PRM_BYTES + 1024;
@@ -58,16 +62,17 @@ MF_DEVINL void act_chunk(float (&v)[N], int act, int nb) {
   }
 }
 
-template <int BLOCK_N, int MODE, int NPW>
-__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE>::CTAS_PER_SM)
+template <int BLOCK_N, int MODE, int NPW, bool SPLIT>
+__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE, SPLIT>::CTAS_PER_SM)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
               const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
   constexpr bool A_TMA = (MODE == MODE_CONV_TMA || MODE == MODE_CONV_TMA_AS);
   constexpr bool A_STAT = (MODE == MODE_CONV_TMA_AS);   // A tile of an m-tile stays resident while all n-tiles stream B
   constexpr int EPI_THREADS = A_TMA ? 128 + NPW * 32 : 128;
-  using C = Cfg2<BLOCK_N, MODE>;
+  using C = Cfg2<BLOCK_N, MODE, SPLIT>;
   constexpr int STAGES = C::STAGES;
   constexpr int LAG = C::LAG;
+  const bool split_out = SPLIT || p.split_out != 0;      // SPLIT == staged hi/lo tiles; narrow tiles store both halves directly
   constexpr int B_STAGE = C::B_STAGE;
   constexpr int NPT = NPW * 32;
   constexpr int RPP = NPT / 8;
@@ -204,6 +209,16 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                 v[i + 2 * e] += f.x;
                 v[i + 2 * e + 1] += f.y;
               }
+              if (split_out) {                                   // residual = hi + lo
+                const uint4 rl = __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo + i));
+                const __half2* rlh = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(rlh[e]);
+                  v[i + 2 * e] += f.x;
+                  v[i + 2 * e + 1] += f.y;
+                }
+              }
             }
           }
         }
@@ -218,6 +233,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
                 sts128(sub + sw128_off(row, (ch & 1) * 4 + (i >> 3)), *reinterpret_cast<uint4*>(o));
+                if constexpr (SPLIT) {
+                  __half2 l[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 h = __half22float2(o[e]);
+                    l[e] = __floats2half2_rn(v[i + 2 * e] - h.x, v[i + 2 * e + 1] - h.y);
+                  }
+                  sts128(sub + C::OUT_HALF + sw128_off(row, (ch & 1) * 4 + (i >> 3)), *reinterpret_cast<uint4*>(l));
+                }
               }
             }
           } else if (mvalid) {
@@ -229,6 +253,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
                 *reinterpret_cast<uint4*>(yp + i) = *reinterpret_cast<uint4*>(o);
+                if (split_out) {
+                  __half2 l[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 h = __half22float2(o[e]);
+                    l[e] = __floats2half2_rn(v[i + 2 * e] - h.x, v[i + 2 * e + 1] - h.y);
+                  }
+                  *reinterpret_cast<uint4*>(yp + p.y_lo + i) = *reinterpret_cast<uint4*>(l);
+                }
               }
             }
           }
@@ -257,10 +290,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 #pragma unroll
             for (int sidx = 0; sidx < BLOCK_N / 64; ++sidx) {
               if (n0 + sidx * 64 < p.Cout) {
-                if (MODE == MODE_DCN)
-                  tma_store_4d(&tmap_y, smem_u32(o_smem + sidx * A_STAGE), n0 + sidx * 64, tile_x0, tile_y0, tile_b);
-                else
-                  tma_store_2d(&tmap_y, smem_u32(o_smem + sidx * A_STAGE), n0 + sidx * 64, m_tile * BM);
+#pragma unroll
+                for (int hl = 0; hl < (SPLIT ? 2 : 1); ++hl) {
+                  const uint32_t src = smem_u32(o_smem + hl * C::OUT_HALF + sidx * A_STAGE);
+                  const int col = n0 + sidx * 64 + hl * p.y_lo;
+                  if (MODE == MODE_DCN)
+                    tma_store_4d(&tmap_y, src, col, tile_x0, tile_y0, tile_b);
+                  else
+                    tma_store_2d(&tmap_y, src, col, m_tile * BM);
+                }
               }
             }
           }
@@ -303,8 +341,17 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           const int k = kb * BK + j * 8;
-          const int tap = k / p.Cin;
-          const int c0 = k - tap * p.Cin;
+          int tap, c0;
+          if (p.split_in) {                 // virtual K order: ((tap, chunk), which in {hi.Whi, lo.Whi, hi.Wlo}, channel)
+            const int unit = k / p.cw, c = k - unit * p.cw;
+            const int tc = unit / 3, which = unit - tc * 3;
+            const int nch = p.Cin / p.cw;
+            tap = tc / nch;
+            c0 = (tc - tap * nch) * p.cw + c + (which == 1 ? p.x_lo : 0);
+          } else {
+            tap = k / p.Cin;
+            c0 = k - tap * p.Cin;
+          }
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           const bool kvalid = k < p.K_real;
           const long long koff = static_cast<long long>(ky * p.W + kx) * p.x_ld + c0;
@@ -378,6 +425,61 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         uint32_t dst_off[PASSES];
 #pragma unroll
         for (int q = 0; q < PASSES; ++q) dst_off[q] = sw128_off(q * RPP + rsub, j);
+        if constexpr (SPLIT) {
+          // strict precision: hi and lo halves of the four corners are blended in fp32 ONCE per (tap, 64-channel chunk) and
+          // feed three consecutive K blocks: hi (x W_hi), lo (x W_hi), hi again (x W_lo).
+          const int lo_bytes = p.x_lo * 2;
+          for (int kb = 0; kb < nkb; kb += 3) {
+            const char* xb = x_img + c0 * 2;
+            const uint32_t rec = (tap * BM + rsub) * 16;
+            uint4 hi4[PASSES], lo4[PASSES];
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+              const float4 wq = lds128f(prm_w + rec + q * RPP * 16);
+              const uint4 o = lds128(prm_o + rec + q * RPP * 16);
+              uint4 vh[4], vl[4];
+              vh[0] = __ldg(reinterpret_cast<const uint4*>(xb + o.x));
+              vh[1] = __ldg(reinterpret_cast<const uint4*>(xb + o.y));
+              vh[2] = __ldg(reinterpret_cast<const uint4*>(xb + o.z));
+              vh[3] = __ldg(reinterpret_cast<const uint4*>(xb + o.w));
+              vl[0] = __ldg(reinterpret_cast<const uint4*>(xb + o.x + lo_bytes));
+              vl[1] = __ldg(reinterpret_cast<const uint4*>(xb + o.y + lo_bytes));
+              vl[2] = __ldg(reinterpret_cast<const uint4*>(xb + o.z + lo_bytes));
+              vl[3] = __ldg(reinterpret_cast<const uint4*>(xb + o.w + lo_bytes));
+              const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+              __half2* oh = reinterpret_cast<__half2*>(&hi4[q]);
+              __half2* ol = reinterpret_cast<__half2*>(&lo4[q]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                unsigned long long acc = f2_pack(0.f, 0.f);
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                  const float2 fh = __half22float2(reinterpret_cast<const __half2*>(&vh[cn])[e]);
+                  const float2 fl = __half22float2(reinterpret_cast<const __half2*>(&vl[cn])[e]);
+                  const unsigned long long w2 = f2_pack(wv[cn], wv[cn]);
+                  acc = f2_fma(w2, f2_pack(fh.x, fh.y), acc);
+                  acc = f2_fma(w2, f2_pack(fl.x, fl.y), acc);
+                }
+                const float2 r2 = f2_unpack(acc);
+                oh[e] = __floats2half2_rn(r2.x, r2.y);
+                const float2 hf = __half22float2(oh[e]);
+                ol[e] = __floats2half2_rn(r2.x - hf.x, r2.y - hf.y);
+              }
+            }
+#pragma unroll
+            for (int which = 0; which < 3; ++which) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              const uint32_t a_stage = smem_u32(a_smem + stage * A_STAGE);
+#pragma unroll
+              for (int q = 0; q < PASSES; ++q) sts128(a_stage + dst_off[q], which == 1 ? lo4[q] : hi4[q]);
+              fence_proxy_async();
+              mbar_arrive(&full_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            c0 += BK;
+            if (c0 >= p.Cin) { c0 = 0; ++tap; }
+          }
+        } else
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t a_stage = smem_u32(a_smem + stage * A_STAGE);
@@ -455,6 +557,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           }
         }
         int tap = 0, c0 = 0, kx = 0, ky = 0;            // running (tap, channel) cursor: no divisions in the K loop
+        int which = 0;                                  // split_in: 0 = A_hi W_hi, 1 = A_lo W_hi, 2 = A_hi W_lo (same A box as 0)
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], (A_TMA && !A_STAT) ? A_STAGE + B_STAGE : B_STAGE);
@@ -462,8 +565,11 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             const uint32_t a_dst = smem_u32(a_smem + stage * A_STAGE);
             for (int jb = 0; jb < nbox; ++jb) {
               const bool valid = tap < ntap;              // K tail: channel coordinate out of range -> TMA zero fill
-              tma_load_im2col_4d(a_dst + jb * box_bytes, &tmap_x, &full_bar[stage], valid ? c0 : p.Cin, cw, chh, cn,
+              tma_load_im2col_4d(a_dst + jb * box_bytes, &tmap_x, &full_bar[stage],
+                                 valid ? c0 + (which == 1 ? p.x_lo : 0) : p.Cin, cw, chh, cn,
                                  static_cast<uint16_t>(valid ? kx : 0), static_cast<uint16_t>(valid ? ky : 0));
+              if (p.split_in && ++which < 3) continue;
+              which = 0;
               c0 += kc;
               if (c0 >= p.Cin) {
                 c0 = 0; ++tap;
@@ -580,11 +686,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, int MODE, int NPW>
+template <int BLOCK_N, int MODE, int NPW, bool SPLIT = false>
 static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx, const IgemmParams& p,
                        int use_tma_store, cudaStream_t st) {
-  using C = Cfg2<BLOCK_N, MODE>;
-  auto kern = igemm2_kernel<BLOCK_N, MODE, NPW>;
+  using C = Cfg2<BLOCK_N, MODE, SPLIT>;
+  auto kern = igemm2_kernel<BLOCK_N, MODE, NPW, SPLIT>;
   static int attr_smem = 0;
   int smem = C::SMEM + g_tunable[MODE == MODE_DCN ? 0 : 1];
   if (smem > 227 * 1024) smem = 227 * 1024;
@@ -611,6 +717,18 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     set_error("dcn igemm: only 3x3 s1 p1 with Cin %% 64 == 0 is built (got Cin=%d)", p.Cin);
     return -1;
   }
+  if (mode == MODE_DCN && (p.split_in != p.split_out || (p.split_in && p.out_mode != OUT_F16_NHWC))) {
+    set_error("dcn igemm: strict precision needs split input AND split fp16 output");
+    return -1;
+  }
+  if (p.split_in && (p.cw <= 0 || p.Cin % p.cw != 0 || (p.cw != 64 && 64 % p.cw != 0) || p.x_lo % 8 != 0)) {
+    set_error("igemm: split input needs Cin %% 64 == 0 or Cin in {8,16,32} and an 8-aligned lo offset (Cin=%d cw=%d)", p.Cin, p.cw);
+    return -1;
+  }
+  if (p.split_out && (p.out_mode != OUT_F16_NHWC || p.y_lo % 8 != 0 || (p.res != nullptr && p.res_lo % 8 != 0))) {
+    set_error("igemm: split output needs fp16 NHWC rows and 8-aligned lo offsets");
+    return -1;
+  }
   if (mode == MODE_CONV && (p.Cin % 8 != 0 || p.x_ld % 8 != 0)) {
     set_error("conv igemm: Cin and pixel stride must be multiples of 8 (got %d, %d)", p.Cin, p.x_ld);
     return -1;
@@ -632,8 +750,8 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
       (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && p.y_ld % 8 == 0) {
     CUresult r;
     if (mode == MODE_DCN) {
-      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cout), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
-                            static_cast<cuuint64_t>(p.B)};
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cout + (p.split_out ? p.y_lo : 0)), static_cast<cuuint64_t>(p.W),
+                            static_cast<cuuint64_t>(p.H), static_cast<cuuint64_t>(p.B)};
       cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.y_ld) * 2, static_cast<cuuint64_t>(p.y_ld) * 2 * p.W,
                             static_cast<cuuint64_t>(p.y_ld) * 2 * p.W * p.H};
       cuuint32_t box[4] = {64, 16, 8, 1};
@@ -641,7 +759,7 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
       r = enc(&ty, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, p.y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.Cout), static_cast<cuuint64_t>(p.M)};
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.Cout + (p.split_out ? p.y_lo : 0)), static_cast<cuuint64_t>(p.M)};
       cuuint64_t gstr[1] = {static_cast<cuuint64_t>(p.y_ld) * 2};
       cuuint32_t box[2] = {64, BM};
       cuuint32_t estr[2] = {1, 1};
@@ -656,14 +774,15 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
   bool a_tma = false;
   IgemmParams pp = p;
   const int kc = p.Cin % 64 == 0 ? 64 : p.Cin;
+  if (p.split_in && kc != 64 && g_tunable[5] != 0) { set_error("igemm: small-C im2col TMA is not built for split input"); return -1; }
   // im2col boxes narrower than 128 B are request-bound inside the TMA unit (measured: the 7x7 stem 1.8x slower than the
   // cp.async gather), so they stay on the gather producers unless tunable 5 asks for them.
   if (mode == MODE_CONV && (kc == 64 || ((kc == 32 || kc == 16 || kc == 8) && g_tunable[5] != 0)) && g_tunable[4] == 0 &&
       (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && p.kw <= 16 && p.kh <= 16 && p.stride <= 8) {
     PFN_encodeIm2col enc2 = encode_im2col_fn();
     if (!enc2) return -1;
-    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H),
-                          static_cast<cuuint64_t>(p.B)};
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Cin + (p.split_in ? p.x_lo : 0)), static_cast<cuuint64_t>(p.W),
+                          static_cast<cuuint64_t>(p.H), static_cast<cuuint64_t>(p.B)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.x_ld) * 2, static_cast<cuuint64_t>(p.x_ld) * 2 * p.W,
                           static_cast<cuuint64_t>(p.x_ld) * 2 * p.W * p.H};
     int lower[2] = {-p.pad, -p.pad};
@@ -680,6 +799,15 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     pp.kc = kc;
   }
   const int ntn_host = (p.Cout + bn - 1) / bn;
+  if (p.split_out && use_tma_store) {          // staged hi/lo tiles: the SPLIT instantiations (N tiles of 64 / 128 only)
+    if (mode == MODE_DCN && bn == 64) return launch2_cfg<64, MODE_DCN, 16, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (mode == MODE_DCN && bn == 128) return launch2_cfg<128, MODE_DCN, 16, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (a_tma && bn == 64) return launch2_cfg<64, MODE_CONV_TMA, 4, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (a_tma && bn == 128) return launch2_cfg<128, MODE_CONV_TMA, 4, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (bn == 64) return launch2_cfg<64, MODE_CONV, 4, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (bn == 128) return launch2_cfg<128, MODE_CONV, 4, true>(tw, ty, tx, pp, use_tma_store, st);
+  }
+  if (mode == MODE_DCN && p.split_in) { set_error("dcn igemm: strict precision needs the staged TMA-store epilogue"); return -1; }
 #define MF_DISPATCH2(BN)                                                                          \
   if (bn == BN) {                                                                                 \
     if (mode == MODE_DCN) return launch2_cfg<BN, MODE_DCN, 8>(tw, ty, tx, pp, use_tma_store, st);  \

@@ -33,6 +33,13 @@ struct IgemmParams {
   int out_mode;
   void* y;
   int y_ld;
+  // strict-precision ("split") operands: an fp32-grade value v is stored as two fp16 numbers hi = fp16(v), lo = fp16(v - hi)
+  // in the same pixel row, the lo block `*_lo` elements after the hi block. split_in: A and the packed weights are split and
+  // the K axis is the concatenation, per (tap, 64-channel chunk), of the three products A_hi W_hi, A_lo W_hi, A_hi W_lo
+  // (K_real / nkb already count that tripling). split_out: the fp16 NHWC output (and the residual) are hi/lo pairs.
+  int split_in, split_out;
+  int x_lo, res_lo, y_lo;
+  int cw;       // split_in: channels per chunk = min(Cin, 64)
 };
 
 int igemm_block_n(int cout);

@@ -74,6 +74,20 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
 int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                             __half* out, cudaStream_t st);
+// strict-precision (hi/lo fp16 pairs) companions, mf_split.cu
+int launch_pack_conv_weight_split(const float* w, int Cout, int Cin, int kh, int kw, int n_pad, int k_pad, __half* out,
+                                  cudaStream_t st);
+int launch_pack_image_split(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st);
+int launch_maxpool2_split(const __half* x, int x_lo, __half* y, int y_lo, int B, int H, int W, int C, int x_ld, int y_ld,
+                          cudaStream_t st);
+int launch_upsample_add_split(const __half* x, int x_lo, const float* w, const __half* skip, int skip_lo, __half* y, int y_lo,
+                              int B, int Hi, int Wi, int C, int f, int x_ld, int skip_ld, int y_ld, cudaStream_t st);
+int launch_edge_gather_split(const __half* feat, int feat_ld, int feat_lo, int ch_a, int ch_b, const long long* edge_idx,
+                             __half* ea, __half* eb, int B, int H, int W, int K, int out_w, int out_h, cudaStream_t st);
+int launch_edge_head_add_split(const __half* t, int t_ld, int t_lo, const float* w, const float* bias, int n_out,
+                               const long long* edge_idx, const long long* edge_len, float* out, int out_ctot, int out_ch0, int B,
+                               int K, int H, int W, cudaStream_t st);
+int launch_split_to_nchw(const __half* x, int x_ld, int x_lo, float* y, int B, int C, int HW, cudaStream_t st);
 int launch_dcn_v2_forward_f32(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                               float* y, int B, int Cin, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph,
                               int pw, int dh, int dw, int dg, cudaStream_t st);

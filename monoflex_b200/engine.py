@@ -13,9 +13,24 @@ import torch
 
 from . import _lib
 
+import os
+
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_OFFMASK = 0, 1, 2, 3
 OUT_F16_NHWC, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
 BN_EPS = 1e-5
+
+PRECISIONS = ("strict", "fast")
+
+
+def default_precision():
+    """Inference arithmetic (DESIGN.md §4 "Precision modes"): 'strict' (default) = every activation / weight an fp16 hi/lo
+    pair, three tensor-core products per K step, fp32-grade results (<= 1e-3 of the reference end to end, the parity
+    contract); 'fast' = one fp16 product (2-4e-3 end to end). `MF_PRECISION` overrides the default; a model can be switched
+    with `KeypointDetector.set_precision()`."""
+    p = os.environ.get("MF_PRECISION", "strict")
+    if p not in PRECISIONS:
+        raise ValueError("MF_PRECISION must be one of %s" % (PRECISIONS,))
+    return p
 
 
 class Act(object):
@@ -27,6 +42,7 @@ class Act(object):
         self.owner = None    # concat group this activation is a slice of
         self.ch_off = 0
         self.npar = 0        # > 0: planar stem layout with `npar` column parities (16-byte pixels)
+        self.split = False   # strict precision: rows are [hi channels | lo channels], lo block `lo` elements after hi
 
     @property
     def M(self):
@@ -39,6 +55,11 @@ class Act(object):
     def ptr(self):
         return self.buf.data_ptr() + 2 * self.ch_off
 
+    @property
+    def lo(self):
+        """element offset of the lo block of a split activation (0 for plain fp16 activations)"""
+        return self.buf.shape[1] // 2 if self.split else 0
+
     def nchw_view(self):
         """torch view [B,C,H,W] of this activation (zero-copy, channels-last strides, for NHWC rows; a reshaped copy for
         the planar stem layout [B][H][C/8 x npar][W/npar][8])."""
@@ -46,17 +67,28 @@ class Act(object):
             P, Wg = self.C // 8, self.W // self.npar
             v = self.buf.view(self.B, self.H, P, self.npar, Wg, 8).permute(0, 2, 5, 1, 4, 3)
             return v.reshape(self.B, self.C, self.H, self.W)
+        if self.split:
+            # hi + lo as a fresh fp32 NCHW tensor (one small kernel); `_mf_act` lets the predictor find the pair rows again
+            out = torch.empty(self.B, self.C, self.H, self.W, dtype=torch.float32, device=self.buf.device)
+            _lib.call("mf_split_to_nchw_f32", self.ptr(), self.ld, self.lo, out.data_ptr(), self.B, self.C, self.H * self.W,
+                      _lib.stream())
+            out._mf_act = self
+            return out
         return self.buf.view(self.B, self.H, self.W, -1)[..., self.ch_off:self.ch_off + self.C].permute(0, 3, 1, 2)
 
 
 class Plan(object):
-    def __init__(self, device, train=False):
-        """train=True: every conv/DCN followed by a normalisation layer is emitted as a raw convolution + the training-mode
+    def __init__(self, device, train=False, strict=False):
+        """strict=True: strict-precision inference plan (hi/lo fp16 pairs, csrc/mf_split.cu + the split paths of
+        csrc/mf_igemm2.cu). train=True: every conv/DCN followed by a normalisation layer is emitted as a raw convolution + the training-mode
         BatchNorm kernels (batch statistics, running-stat update, fused residual + activation; csrc/mf_bn_train.cu) instead
         of folding eval statistics into the GEMM epilogue. `bn_saved` lists (module, raw, y, stats) per layer for a backward
         tape. Forward only so far ("Training tape")."""
         self.device = device
         self.train = train
+        self.strict = strict
+        if strict and train:
+            raise NotImplementedError("strict precision is an inference mode; training plans run the fp16 kernels")
         self.bn_saved = []
         self.tape = []       # train mode: one record per emitted layer, consumed in reverse by monoflex_b200/tape.py
         self.acts = []
@@ -67,8 +99,9 @@ class Plan(object):
         self.n_launch = 0
 
     # ---- symbolic construction
-    def act(self, B, H, W, C):
+    def act(self, B, H, W, C, split=None):
         a = Act(B, H, W, C)
+        a.split = self.strict if split is None else split
         self.acts.append(a)
         return a
 
@@ -76,10 +109,11 @@ class Plan(object):
         """Return an Act that is the channel concatenation of `parts`, placing every part as a slice of one buffer."""
         B, H, W = parts[0].B, parts[0].H, parts[0].W
         total = sum(p.C for p in parts)
-        cat = self.act(B, H, W, total)
+        cat = self.act(B, H, W, total, split=parts[0].split)
         off = 0
         for p in parts:
             assert p.owner is None and (p.B, p.H, p.W) == (B, H, W), "activation already placed in another concat"
+            assert p.split == cat.split
             p.owner, p.ch_off = cat, off
             off += p.C
         return cat
@@ -93,7 +127,7 @@ class Plan(object):
                 if a.npar:
                     a.buf = torch.empty(a.M * a.C // 8, 8, dtype=torch.half, device=self.device)
                 else:
-                    a.buf = torch.empty(a.M, a.C, dtype=torch.half, device=self.device)
+                    a.buf = torch.empty(a.M, (2 if a.split else 1) * a.C, dtype=torch.half, device=self.device)
         for a in self.acts:
             if a.owner is not None:
                 root, off = a, 0
@@ -129,8 +163,9 @@ class Plan(object):
         return [(name, args, a.elapsed_time(b)) for name, args, a, b in evs]
 
     # ---- parameter preparation
-    def pack_weight(self, w, cin_pad=None):
-        """OIHW (or OIW for Conv1d) fp32 parameter -> packed fp16 [n_pad, k_pad] device tensor."""
+    def pack_weight(self, w, cin_pad=None, split=False):
+        """OIHW (or OIW for Conv1d) fp32 parameter -> packed fp16 [n_pad, k_pad] device tensor. split=True: hi/lo pair
+        weights in the tripled virtual K order of a split-input GEMM (mf_pack_conv_weight_split)."""
         w = w.detach().float().contiguous()
         if w.dim() == 3:
             w = w.unsqueeze(2)   # Conv1d: [O, I, 1, k]
@@ -138,6 +173,13 @@ class Plan(object):
         cin_pad = cin if cin_pad is None else cin_pad
         bn = _lib.load().mf_conv_block_n(cout)
         n_pad = (cout + bn - 1) // bn * bn
+        if split:
+            assert cin_pad == cin
+            k_pad = (3 * kh * kw * cin + 63) // 64 * 64
+            out = torch.empty(n_pad, k_pad, dtype=torch.half, device=self.device)
+            _lib.call("mf_pack_conv_weight_split", w.data_ptr(), cout, cin, kh, kw, n_pad, k_pad, out.data_ptr(), _lib.stream())
+            self.keep.append(out)
+            return out, n_pad, k_pad
         k_pad = (kh * kw * cin_pad + 63) // 64 * 64
         out = torch.empty(n_pad, k_pad, dtype=torch.half, device=self.device)
         _lib.call("mf_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr(),
@@ -197,7 +239,7 @@ class Plan(object):
             self.tape.append(dict(kind="conv_bn", x=x, weight=weight, bias=bias, stride=stride, pad=pad, raw=raw, y=y, act=act,
                                   residual=residual, abs_weight=abs_weight, bn=self.bn_saved[first:]))
             return y
-        wp, n_pad, k_pad = self.pack_weight(weight, cin_pad)
+        wp, n_pad, k_pad = self.pack_weight(weight, cin_pad, split=x.split)
         scale, shift = self.affine(cout, n_pad, bn, bias, abs_weight)
         Ho = (x.H + 2 * pad[0] - kh) // stride + 1 if isinstance(pad, tuple) else (x.H + 2 * pad - kh) // stride + 1
         Wo = (x.W + 2 * pad[1] - kw) // stride + 1 if isinstance(pad, tuple) else (x.W + 2 * pad - kw) // stride + 1
@@ -205,6 +247,14 @@ class Plan(object):
         y = out if out is not None else self.act(x.B, Ho, Wo, cout)
         assert (y.H, y.W, y.C) == (Ho, Wo, cout)
         cin = x.C
+        if x.split or y.split:
+            assert residual is None or residual.split == y.split
+            self.add("mf_conv2d_nhwc_f16x2", lambda: (
+                x.ptr(), x.ld, x.lo, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
+                scale.data_ptr(), shift.data_ptr(), residual.ptr() if residual is not None else None,
+                residual.ld if residual is not None else 0, residual.lo if residual is not None else 0, act, OUT_F16_NHWC,
+                y.ptr(), y.ld, y.lo, 1 if x.split else 0, 1 if y.split else 0))
+            return y
         self.add("mf_conv2d_nhwc_f16", lambda: (
             x.ptr(), x.ld, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
             scale.data_ptr(), shift.data_ptr(), residual.ptr() if residual is not None else None,
@@ -214,9 +264,14 @@ class Plan(object):
     def conv_to_f32(self, x, weight, bias, out_tensor, out_mode, act, y_ld, stride=1, pad=0, bn=None):
         """conv whose result leaves the NHWC fp16 world: fp32 NHWC rows (offset/mask) or fp32 NCHW maps (heads)."""
         cout, _, kh, kw = weight.shape
-        wp, n_pad, k_pad = self.pack_weight(weight)
+        wp, n_pad, k_pad = self.pack_weight(weight, split=x.split)
         scale, shift = self.affine(cout, n_pad, bn, bias)
         cin = x.C
+        if x.split:
+            self.add("mf_conv2d_nhwc_f16x2", lambda: (
+                x.ptr(), x.ld, x.lo, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
+                scale.data_ptr(), shift.data_ptr(), None, 0, 0, act, out_mode, out_tensor.data_ptr(), y_ld, 0, 1, 0))
+            return
         self.add("mf_conv2d_nhwc_f16", lambda: (
             x.ptr(), x.ld, x.B, x.H, x.W, cin, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
             scale.data_ptr(), shift.data_ptr(), None, 0, act, out_mode, out_tensor.data_ptr(), y_ld))
@@ -228,8 +283,16 @@ class Plan(object):
         self.conv_to_f32(x, dcn_mod.conv_offset_mask.weight, dcn_mod.conv_offset_mask.bias, om, OUT_F32_NHWC,
                          ACT_OFFMASK, 32, stride=1, pad=1)
         cout = dcn_mod.weight.shape[0]
-        wp, n_pad, k_pad = self.pack_weight(dcn_mod.weight)
+        wp, n_pad, k_pad = self.pack_weight(dcn_mod.weight, split=x.split)
         cin = x.C
+        if x.split:
+            scale, shift = self.affine(cout, n_pad, bn, dcn_mod.bias)
+            y = out if out is not None else self.act(x.B, x.H, x.W, cout)
+            assert y.split
+            self.add("mf_dcn_nhwc_f16x2", lambda: (
+                x.ptr(), x.ld, x.lo, x.B, x.H, x.W, cin, om.data_ptr(), 32, wp.data_ptr(), n_pad, k_pad, cout, scale.data_ptr(),
+                shift.data_ptr(), ACT_RELU, y.ptr(), y.ld, y.lo))
+            return y
         if self.train:
             scale, shift = self.affine(cout, n_pad, None, dcn_mod.bias)
             raw = self.act(x.B, x.H, x.W, cout)
@@ -273,6 +336,10 @@ class Plan(object):
 
     def maxpool2(self, x, out=None):
         y = out if out is not None else self.act(x.B, x.H // 2, x.W // 2, x.C)
+        if x.split:
+            assert y.split
+            self.add("mf_maxpool2_split", lambda: (x.ptr(), x.lo, y.ptr(), y.lo, x.B, x.H, x.W, x.C, x.ld, y.ld))
+            return y
         self.add("mf_maxpool2_nhwc_f16", lambda: (x.ptr(), y.ptr(), x.B, x.H, x.W, x.C, x.ld, y.ld))
         if self.train:
             self.tape.append(dict(kind="maxpool2", x=x, y=y))
@@ -285,6 +352,12 @@ class Plan(object):
         wt = up_weight.detach().float().reshape(C, k * k).t().contiguous()   # [k*k, C]
         self.keep.append(wt)
         y = self.act(x.B, x.H * f, x.W * f, C)
+        if x.split:
+            assert y.split and (skip is None or skip.split)
+            self.add("mf_upsample_add_split", lambda: (
+                x.ptr(), x.lo, wt.data_ptr(), skip.ptr() if skip is not None else None, skip.lo if skip is not None else 0,
+                y.ptr(), y.lo, x.B, x.H, x.W, C, f, x.ld, skip.ld if skip is not None else 0, y.ld))
+            return y
         self.add("mf_upsample_add_nhwc_f16", lambda: (
             x.ptr(), wt.data_ptr(), skip.ptr() if skip is not None else None, y.ptr(), x.B, x.H, x.W, C, f, x.ld,
             skip.ld if skip is not None else 0, y.ld))

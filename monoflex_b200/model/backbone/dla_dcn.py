@@ -131,7 +131,21 @@ class DLA(nn.Module):
         rows_ok = (len(self.level0) == 3 and len(self.level1) == 3 and self.channels[0] == 16 and x8.W % 2 == 0 and
                    self.level1[0].stride[0] == 2 and os.environ.get("MF_NO_ROWS_STEM", "0") != "1" and not P.train)
         y = []
-        if rows_ok:
+        if P.strict:
+            # strict precision: x8 is the 16-channel pair-packed image [hi3 | lo3 | hi3 | 0 x 7] (mf_pack_image_split), so the
+            # 7x7 stem is a plain 16-channel conv whose per-tap weights are [W_hi | W_hi | W_lo | 0]: the three split products
+            # A_hi W_hi + A_lo W_hi + A_hi W_lo in one pass. Its output and everything after it are hi/lo pairs.
+            w = self.base_layer[0].weight.detach().float()
+            w_hi = w.half().float()
+            w_lo = (w - w_hi).half().float()
+            w16 = torch.zeros(w.shape[0], 16, w.shape[2], w.shape[3], dtype=torch.float32, device=w.device)
+            w16[:, 0:3], w16[:, 3:6], w16[:, 6:9] = w_hi, w_hi, w_lo
+            x = P.conv(x8, w16, 1, 3, self.base_layer[1])
+            for seq in (self.level0, self.level1):
+                for i in range(0, len(seq), 3):
+                    x = P.conv(x, seq[i].weight, seq[i].stride[0], 1, seq[i + 1])
+                y.append(x)
+        elif rows_ok:
             # full-resolution stem on 16-byte-pixel planes: no im2col copies (csrc/mf_rows.cu)
             x8.npar = 1
             a0 = P.conv_rows(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], out_planar=True, out_npar=1)
@@ -238,8 +252,9 @@ class DLASeg(nn.Module):
 
     # ---- plan construction / execution
     def build_plan(self, B, H, W, device):
-        P = engine.Plan(device, train=self.training)
-        x8 = P.act(B, H, W, 8)
+        strict = (not self.training) and self._precision() == "strict"
+        P = engine.Plan(device, train=self.training, strict=strict)
+        x8 = P.act(B, H, W, 16, split=False) if strict else P.act(B, H, W, 8)
         levels = self.base.plan(P, x8)
         ups = self.dla_up.plan(P, levels)
         y = [ups[i] for i in range(self.last_level - self.first_level)]   # the reference's .clone()s are not needed
@@ -248,8 +263,12 @@ class DLASeg(nn.Module):
         P.input, P.output, P.levels, P.ups = x8, y[-1], levels, ups
         return P
 
+    def _precision(self):
+        """'strict' | 'fast' (engine.default_precision unless KeypointDetector.set_precision / self.precision says otherwise)"""
+        return getattr(self, "precision", None) or engine.default_precision()
+
     def _plan_for(self, x):
-        key = (tuple(x.shape), engine.fingerprint(self))
+        key = (tuple(x.shape), engine.fingerprint(self), self._precision())
         plan = self._plans.get('plan')
         if plan is None or self._plans.get('key') != key:
             B, _, H, W = x.shape
@@ -258,8 +277,9 @@ class DLASeg(nn.Module):
         return plan
 
     def forward(self, x):
-        """x: [B,3,H,W] fp32 NCHW (reference signature). Returns the [B,64,H/4,W/4] feature map as a zero-copy
-        channels-last fp16 view of the plan's output buffer."""
+        """x: [B,3,H,W] fp32 NCHW (reference signature). Returns the [B,64,H/4,W/4] feature map: fast mode a zero-copy
+        channels-last fp16 view of the plan's output buffer; strict mode an fp32 tensor (hi + lo) that remembers its pair
+        rows (`_mf_act`) so that the predictor consumes them without a conversion."""
         if self.training:
             raise NotImplementedError("monoflex_b200 round 1 builds the inference path; the fused training path "
                                       "(SURVEY §8 rows R5/R11-R13) is not built yet - there is no PyTorch fallback")
@@ -284,6 +304,6 @@ class DLASeg(nn.Module):
 
     def run_plan(self, plan, x):
         B, C, H, W = x.shape
-        call("mf_pack_image", x.data_ptr(), plan.input.ptr(), B, C, H, W, stream())
+        call("mf_pack_image_split" if plan.strict else "mf_pack_image", x.data_ptr(), plan.input.ptr(), B, C, H, W, stream())
         plan.run()
         self.last_plan = plan

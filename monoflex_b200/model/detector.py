@@ -24,6 +24,17 @@ class KeypointDetector(nn.Module):
         self.test = cfg.DATASETS.TEST_SPLIT == 'test'
         self.use_cuda_graph = os.environ.get("MF_CUDA_GRAPH", "1") != "0"
         self._graph = None
+        self.set_precision(engine.default_precision())
+
+    def set_precision(self, mode):
+        """'strict' (default): hi/lo fp16 pair arithmetic, fp32-grade results - the mode that meets the 1e-3 parity contract
+        with the fp32 reference; 'fast': single fp16 tensor-core pass (2-4e-3 end to end). Inference only; training plans
+        always run the fp16 kernels with fp32 master weights."""
+        if mode not in engine.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (engine.PRECISIONS,))
+        self.precision = self.backbone.precision = mode
+        self._graph = None
+        return self
 
     def forward(self, images, targets=None):
         if self.training and targets is None:
@@ -74,7 +85,7 @@ class KeypointDetector(nn.Module):
         post.check_config()
         x = x.float().contiguous()
         k_edge = targets[0].get_field("edge_indices").shape[0]
-        key = (tuple(x.shape), x.device, k_edge, engine.fingerprint(self), post.det_threshold, post.max_detection)
+        key = (tuple(x.shape), x.device, k_edge, engine.fingerprint(self), post.det_threshold, post.max_detection, self.precision)
         g = self._graph
         if g is None or g['key'] != key:
             g = self._capture(x, targets, key)
@@ -91,7 +102,7 @@ class KeypointDetector(nn.Module):
         pred, post = self.heads.predictor, self.heads.post_processor
         xs = x.clone()
         plan_b = self.backbone._plan_for(xs)
-        plan_h = pred.plan_for(plan_b.output.nchw_view(), key[2])
+        plan_h = pred.plan_for(plan_b.output, key[2])
         pred.load_targets(plan_h, targets)
         meta = tuple(t.clone() for t in post.prepare_targets(targets, self.test, x.device))
 

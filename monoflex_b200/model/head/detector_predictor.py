@@ -76,7 +76,8 @@ class _predictor(nn.Module):
     def build_plan(self, feat, K_edge):
         """feat: engine.Act-like description of the [B,H,W,64] fp16 feature rows."""
         dev = feat.buf.device
-        P = engine.Plan(dev, train=self.training)
+        strict = bool(getattr(feat, "split", False))
+        P = engine.Plan(dev, train=self.training, strict=strict)
         B, H, W, hc = feat.B, feat.H, feat.W, self.head_conv
         x = P.act(B, H, W, feat.C)
         x.buf, x.ch_off, x.owner = feat.buf, feat.ch_off, None
@@ -103,7 +104,9 @@ class _predictor(nn.Module):
             off_ch0 = ch0s[self.offset_index[0]] + sum(h.weight.shape[0] for h in
                                                        list(self.reg_heads[self.offset_index[0]])[:self.offset_index[1]])
         import os
-        fused = not P.train and os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
+        # strict precision runs the generic split GEMMs: the nine 3x3 convs as one N = 2304 layer whose hi/lo hidden map goes
+        # through HBM once (2.3 GB at B = 8), then the 1x1 heads on its channel slices
+        fused = not P.train and not strict and os.environ.get("MF_NO_FUSED_HEAD", "0") != "1" and hc == 256 and feat.C % 64 == 0 and \
             all(sum(h.weight.shape[0] for h in heads) <= 32 for heads in self.reg_heads) and self.num_classes <= 32
         if fused:
             # ---- one kernel: 9 x (3x3 conv + IABN) + every 1x1 head; hidden activations stay on chip (csrc/mf_head.cu)
@@ -182,8 +185,12 @@ class _predictor(nn.Module):
             ea = P.act(B, 1, K_edge + 2, hc)
             eb = P.act(B, 1, K_edge + 2, hc)
             ow, oh = self.output_width, self.output_height
-            P.add("mf_edge_gather", lambda: (hid.ptr(), hid.ld, edge_cols[0], edge_cols[1], P.edge_idx.data_ptr(), ea.ptr(),
-                                              eb.ptr(), B, H, W, K_edge, ow, oh))
+            if strict:
+                P.add("mf_edge_gather_split", lambda: (hid.ptr(), hid.ld, hid.lo, edge_cols[0], edge_cols[1],
+                                                        P.edge_idx.data_ptr(), ea.ptr(), eb.ptr(), B, H, W, K_edge, ow, oh))
+            else:
+                P.add("mf_edge_gather", lambda: (hid.ptr(), hid.ld, edge_cols[0], edge_cols[1], P.edge_idx.data_ptr(), ea.ptr(),
+                                                  eb.ptr(), B, H, W, K_edge, ow, oh))
             for src, seq, dst, ch0, ctot in ((ea, self.trunc_heatmap_conv, cls, 0, self.num_classes),
                                              (eb, self.trunc_offset_conv, reg, off_ch0, self.num_reg)):
                 t = P.conv(src, seq[0].weight, 1, 0, seq[1], bias=seq[0].bias, act=engine.ACT_NONE)   # [B,1,K,256]
@@ -191,9 +198,14 @@ class _predictor(nn.Module):
                 b2 = seq[3].bias.detach().float().contiguous()
                 P.keep.extend([w2, b2])
                 n_out = w2.shape[0]
-                P.add("mf_edge_head_add", lambda t=t, w2=w2, b2=b2, n_out=n_out, dst=dst, ch0=ch0, ctot=ctot: (
-                    t.ptr(), w2.data_ptr(), b2.data_ptr(), n_out, P.edge_idx.data_ptr(), P.edge_len.data_ptr(),
-                    dst.data_ptr(), ctot, ch0, B, K_edge, H, W))
+                if strict:
+                    P.add("mf_edge_head_add_split", lambda t=t, w2=w2, b2=b2, n_out=n_out, dst=dst, ch0=ch0, ctot=ctot: (
+                        t.ptr(), t.ld, t.lo, w2.data_ptr(), b2.data_ptr(), n_out, P.edge_idx.data_ptr(), P.edge_len.data_ptr(),
+                        dst.data_ptr(), ctot, ch0, B, K_edge, H, W))
+                else:
+                    P.add("mf_edge_head_add", lambda t=t, w2=w2, b2=b2, n_out=n_out, dst=dst, ch0=ch0, ctot=ctot: (
+                        t.ptr(), w2.data_ptr(), b2.data_ptr(), n_out, P.edge_idx.data_ptr(), P.edge_len.data_ptr(),
+                        dst.data_ptr(), ctot, ch0, B, K_edge, H, W))
         n_cls = cls.numel()
         P.add("mf_sigmoid_clamp", lambda: (cls.data_ptr(), n_cls))
         P.finalize()
@@ -207,7 +219,7 @@ class _predictor(nn.Module):
     def plan_for(self, features, K_edge):
         feat = _as_rows(features)
         key = (feat.buf.data_ptr(), feat.ch_off, feat.B, feat.H, feat.W, feat.buf.shape[1], K_edge,
-               engine.fingerprint(self))
+               engine.fingerprint(self), bool(getattr(feat, "split", False)))
         plan = self._plans.get('plan')
         if plan is None or self._plans.get('key') != key:
             plan = self.build_plan(feat, K_edge)
@@ -245,11 +257,16 @@ class _Rows(object):
 
 def _as_rows(features):
     """Accept the backbone's zero-copy channels-last fp16 view, or any [B,C,H,W] CUDA tensor (converted by a kernel)."""
+    act = features if isinstance(features, engine.Act) else getattr(features, "_mf_act", None)
+    if act is not None:                          # the backbone plan's own output rows (strict precision: hi/lo pairs)
+        r = _Rows()
+        r.B, r.H, r.W, r.C, r.ch_off, r.buf, r.split = act.B, act.H, act.W, act.C, act.ch_off, act.buf, act.split
+        return r
     if not features.is_cuda:
         raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
     B, C, H, W = features.shape
     r = _Rows()
-    r.B, r.H, r.W, r.C, r.ch_off = B, H, W, C, 0
+    r.B, r.H, r.W, r.C, r.ch_off, r.split = B, H, W, C, 0, False
     if features.dtype == torch.half and features.stride(1) == 1 and features.stride(3) % 8 == 0 and \
             features.stride(2) == W * features.stride(3) and features.stride(0) == H * features.stride(2):
         ld = features.stride(3)

@@ -35,6 +35,15 @@ def to_rows(x_nchw, c_pad=None):
     return rows.cuda()
 
 
+def to_rows_split(x_nchw):
+    """[B,C,H,W] fp32 -> [B*H*W, 2C] fp16 pair rows [hi | lo] (strict-precision activation layout)"""
+    B, C, H, W = x_nchw.shape
+    r = x_nchw.permute(0, 2, 3, 1).reshape(-1, C).float()
+    hi = r.half()
+    lo = (r - hi.float()).half()
+    return torch.cat([hi, lo], 1).cuda()
+
+
 def from_rows(act):
     """engine.Act -> [B,C,H,W] fp32 CPU"""
     return act.nchw_view().float().cpu().contiguous()

@@ -1,10 +1,10 @@
 """-m gpu: whole-path parity (DLA-34 + IDA-up + DCNv2 + predictor + decode) through the reference-facing module API.
 
-Tolerances: the fast path stores activations / weights in fp16 with fp32 accumulation. Each kernel is
-within 1e-3 of fp32 on identical operands (test_gpu_ops.py); end to end, ~50 stacked layers accumulate
-rounding noise to ~2-4e-3 of max|ref| on this synthetic network (measured with a CPU emulation of the same rounding
-points), so the end-to-end bound asserted here is 1e-2 vs the fp32 oracle / reference golden, and the decode stage is
-checked bit-exactly on the GPU's own head outputs."""
+Tolerances (DESIGN.md §4 "Precision modes"): the DEFAULT mode is strict precision (hi/lo fp16 pairs, three tensor-core
+products per K step, fp32-grade): it has to meet the north star's contract, max|a-b| / max|b| <= 1e-3 per tensor against
+the fp32 oracle / the unmodified reference's golden, end to end (E2E_TOL). The opt-in fast mode (one fp16 product, fp16
+activation storage) accumulates the rounding of ~50 stacked layers to 2-4e-3 on this synthetic network and is held to
+FAST_TOL = 1e-2. The decode stage is checked bit-exactly on the GPU's own head outputs in both."""
 import os
 
 import numpy as np
@@ -13,20 +13,27 @@ import torch
 
 from conftest import GOLDEN
 from gpu_util import rel_err, set_impl
+from test_gpu_ops import assert_decode_columns
 from monoflex_b200 import synthetic as syn
 from monoflex_b200.config import default_cfg
 from monoflex_b200.model.detector import KeypointDetector
 from oracle import monoflex_oracle as mo
 
 pytestmark = pytest.mark.gpu
-E2E_TOL = 1e-2
+E2E_TOL = 1e-3          # strict precision = the parity contract
+FAST_TOL = 1e-2         # opt-in fast mode
+MODES = [("strict", 0), ("fast", 0), ("fast", 1)]        # (precision, conv implementation: 1 = CUDA-core cross-check)
 
 
-def build(H, W):
+def tol_of(precision):
+    return E2E_TOL if precision == "strict" else FAST_TOL
+
+
+def build(H, W, precision="strict"):
     sd = syn.make_state_dict(0)
     m = KeypointDetector(default_cfg(width=W, height=H))
     m.load_state_dict(sd)
-    return m.cuda().eval(), sd
+    return m.cuda().eval().set_precision(precision), sd
 
 
 @pytest.fixture(scope="module")
@@ -39,9 +46,10 @@ def small():
     return m, sd, x, tg, targets
 
 
-@pytest.mark.parametrize("impl", [1, 0])
-def test_backbone_levels_vs_oracle(small, impl):
+@pytest.mark.parametrize("precision,impl", MODES)
+def test_backbone_levels_vs_oracle(small, precision, impl):
     m, sd, x, tg, _ = small
+    m.set_precision(precision)
     set_impl(impl)
     try:
         with torch.no_grad():
@@ -55,14 +63,17 @@ def test_backbone_levels_vs_oracle(small, impl):
             for i, a in enumerate(plan.ups):
                 errs['dla_up%d' % i] = rel_err(a.nchw_view().float().cpu(), taps['dla_up%d' % i])
             errs['features'] = rel_err(feats, fo)
-        print("impl", impl, {k: "%.2e" % v for k, v in errs.items()})
-        assert max(errs.values()) < E2E_TOL, errs
+        print(precision, "impl", impl, {k: "%.2e" % v for k, v in errs.items()})
+        assert max(errs.values()) < tol_of(precision), errs
     finally:
         set_impl(0)
+        m.set_precision("strict")
 
 
-def test_detector_vs_reference_golden(small):
+@pytest.mark.parametrize("precision", ["strict", "fast"])
+def test_detector_vs_reference_golden(small, precision):
     m, sd, x, tg, targets = small
+    m.set_precision(precision)
     with np.load(os.path.join(GOLDEN, "detector_128x256.npz")) as z:
         g = {k: torch.from_numpy(z[k]) for k in z.files}
     with torch.no_grad():
@@ -72,15 +83,19 @@ def test_detector_vs_reference_golden(small):
         feats = m.backbone.last_plan.output.nchw_view().float().cpu()
     e = {'features': rel_err(feats, g['features']), 'cls': rel_err(pred.cls.cpu(), g['cls']),
          'reg': rel_err(pred.reg.cpu(), g['reg'])}
-    print({k: "%.2e" % v for k, v in e.items()})
-    assert max(e.values()) < E2E_TOL, e
+    print(precision, {k: "%.2e" % v for k, v in e.items()})
+    m.set_precision("strict")
+    assert max(e.values()) < tol_of(precision), e
     # decode stage on the GPU's own head outputs: bit-exact integer outputs vs the oracle
     res_o, topk_o = mo.post_process({'cls': pred.cls.cpu(), 'reg': pred.reg.cpu()}, tg['calib_P'], tg['pad_size'],
                                     tg['size'], 0.0)
     s, inds, cls, ys, xs = eval_utils['topk']
     assert torch.equal(inds.cpu(), topk_o[1]) and torch.equal(cls.cpu(), topk_o[2])
     assert result.shape == res_o[0].shape == g['result_thr0.0'].shape
-    assert (result.cpu() - res_o[0]).abs().max() <= 1e-3 * max(1.0, res_o[0].abs().max().item())
+    assert_decode_columns(result.cpu(), res_o[0])
+    # R8 on the product path: the POIs the fused decode kernel gathered from its own `reg` map
+    ws = m.heads.post_processor._ws
+    assert torch.equal(ws.pois.cpu(), mo.gather_pois(pred.reg.cpu(), topk_o[1]))
 
 
 def test_forward_async_matches_forward(small):
@@ -108,11 +123,25 @@ def test_predictor_alone_from_fp32_nchw_features(small):
     assert rel_err(pg['reg'].cpu(), po['reg']) < 2e-3
 
 
-def test_batch_and_full_resolution():
+def test_strict_mode_is_default_and_graph_replay_matches_eager(small):
+    """the default precision is the one that meets the contract; graph replay == eager launches, bit for bit"""
+    m, sd, x, tg, targets = small
+    assert m.precision == "strict" and m.backbone._precision() == "strict"
+    with torch.no_grad():
+        m.heads.post_processor.det_threshold = 0.0
+        r_graph, _, _ = m(x.cuda(), targets)
+        m.use_cuda_graph = False
+        r_eager, _, _ = m(x.cuda(), targets)
+        m.use_cuda_graph = True
+    assert torch.equal(r_graph, r_eager)
+
+
+@pytest.mark.parametrize("precision", ["strict", "fast"])
+def test_batch_and_full_resolution(precision):
     """BASELINE configs[1] shape: B=8, 384x1280. Image 0 is checked against the fp32 oracle (one CPU forward); batch
     independence and determinism are checked as size-independent properties."""
     H, W, B = 384, 1280, 8
-    m, sd = build(H, W)
+    m, sd = build(H, W, precision)
     x = syn.make_images(B, H, W)
     tg = syn.make_targets(B, W // 4, H // 4)
     targets = [t.to("cuda") for t in syn.make_param_lists(tg)]
@@ -133,5 +162,5 @@ def test_batch_and_full_resolution():
         mo.detector_eval(sd, x[:1], tg['edge_indices'][:1], tg['edge_len'][:1], tg['calib_P'][:1], tg['pad_size'][:1],
                          tg['size'][:1], 0.0, taps)
     e = {'cls': rel_err(cls1[:1].cpu(), taps['cls']), 'reg': rel_err(reg1[:1].cpu(), taps['reg'])}
-    print({k: "%.2e" % v for k, v in e.items()})
-    assert max(e.values()) < E2E_TOL, e
+    print(precision, {k: "%.2e" % v for k, v in e.items()})
+    assert max(e.values()) < tol_of(precision), e
