@@ -251,6 +251,15 @@ int mf_loss_backward(const float* pred_cls, const float* hm, const float* pred_r
  * 1-based update count; grads are multiplied by grad_scale first (1/world_size after an NCCL SUM of the arena);
  * lr_scale is the scheduler's multiplier (solver/__init__.py:64-92). One launch, 28 B per parameter. */
 int mf_adamw_chunk(void);
+/* CUDA-graph-safe AdamW step with a finite guard (the reference's optimizer.step(), engine/trainer.py:121, for a training
+ * step captured in one graph): the 1-based step count lives in device memory (state4[0]) instead of being a host scalar;
+ * with check_finite the gradient arena is scanned first and a non-finite gradient SKIPS the update (state4[2] counts the
+ * skipped steps) instead of being written into params / exp_avg / exp_avg_sq. state4: long long[4] zero-initialised by the
+ * caller; dyn16: 16 bytes of device scratch. Three launches: scan, 1-thread prepare (bias corrections in double), update. */
+int mf_adamw_step_dyn(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* chunk_lr,
+                      long long n_chunks, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                      float lr_scale, long long* state4, void* dyn16, int check_finite, void* stream);
+
 /* DDP gradient all-reduce (tools/plain_train_net.py:100-104) FUSED with the AdamW step for world > 1: one kernel over
  * peer-mapped memory. param_ptrs / grad_ptrs: HOST arrays [world] of device addresses of every rank's parameter / gradient
  * arena as mapped into THIS process (symmetric memory / CUDA IPC); mc_params / mc_grads: NVLS multicast addresses of the

@@ -67,6 +67,9 @@ int launch_focal_loss_backward(const float* pred, const float* tgt, long long n,
 int launch_adamw_arena(float* p, const float* g, float* m, float* v, const float* chunk_lr, long long n_chunks,
                        float beta1, float beta2, float eps, float wd, long long step, float grad_scale, float lr_scale,
                        cudaStream_t st);
+int launch_adamw_arena_dyn(float* p, const float* g, float* m, float* v, const float* chunk_lr, long long n_chunks,
+                           float beta1, float beta2, float eps, float wd, float grad_scale, float lr_scale, long long* state4,
+                           void* dyn16, int check_finite, cudaStream_t st);
 int launch_decode(const float* heat, const float* reg, const float* calib, const float* pad, const float* size,
                   const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
                   float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,

@@ -177,6 +177,86 @@ int launch_adamw_arena(float* p, const float* g, float* m, float* v, const float
   return check_cuda(cudaGetLastError(), "adamw_arena");
 }
 
+// ---------------------------------------------------------------- CUDA-graph-safe AdamW step with a finite guard
+// `mf_adamw_step` takes the step count (for the bias corrections) as a host scalar, which a captured graph would freeze.
+// Here the count lives on the device and three launches make one optimiser step:
+//   1. grad_finite_kernel : state[1] |= any non-finite element in the gradient arena (fp16 gradient flow under a loss
+//                           scale can overflow; one inf written by AdamW poisons params, exp_avg and exp_avg_sq for good);
+//   2. adamw_prepare_kernel (1 thread): if the flag is clean, step += 1 and the bias corrections of the new step are
+//                           computed in double (torch computes them in Python doubles); else the step is skipped
+//                           (state[2] += 1). Either way it publishes (bc1, rsqrt_bc2, skip) and clears the flag;
+//   3. adamw_arena_dyn_kernel: the arena update, reading those three values from device memory.
+// state = long long[4]: [0] step count, [1] found-non-finite flag of the current step, [2] skipped steps, [3] unused.
+struct AdamwDyn { float bc1, rsqrt_bc2; int skip, pad; };
+
+__global__ void __launch_bounds__(256) grad_finite_kernel(const float* __restrict__ g, long long n_vec, long long* state) {
+  pdl_wait();
+  bool bad = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    // x - x is 0 for finite x and NaN for inf / NaN
+    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+    bad |= !(t == 0.f);
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicExch(reinterpret_cast<unsigned long long*>(state + 1), 1ull);
+}
+__global__ void adamw_prepare_kernel(long long* state, AdamwDyn* dyn, float beta1, float beta2, int check) {
+  pdl_wait();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool skip = check != 0 && state[1] != 0;
+  if (skip) state[2] += 1; else state[0] += 1;
+  state[1] = 0;
+  const double step = static_cast<double>(state[0] < 1 ? 1 : state[0]);
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  dyn->bc1 = static_cast<float>(bc1);
+  dyn->rsqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  dyn->skip = skip ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) adamw_arena_dyn_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                              float* __restrict__ m, float* __restrict__ v,
+                                                              const float* __restrict__ chunk_lr, long long n_chunks,
+                                                              AdamwConsts k, const AdamwDyn* __restrict__ dyn) {
+  pdl_wait();
+  if (dyn->skip) return;
+  k.bc1 = dyn->bc1;
+  k.rsqrt_bc2 = dyn->rsqrt_bc2;
+  constexpr int VEC_PER_CHUNK = MF_ADAMW_CHUNK / 4;
+  const long long n_vec = n_chunks * VEC_PER_CHUNK;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float lr = __ldg(chunk_lr + i / VEC_PER_CHUNK) * k.lr_scale;
+    if (lr == 0.f) continue;
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_update4(pp, gg, mm, vv, lr, k);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+int launch_adamw_arena_dyn(float* p, const float* g, float* m, float* v, const float* chunk_lr, long long n_chunks,
+                           float beta1, float beta2, float eps, float wd, float grad_scale, float lr_scale, long long* state4,
+                           void* dyn16, int check_finite, cudaStream_t st) {
+  if (n_chunks <= 0) return 0;
+  const long long n_vec = n_chunks * (MF_ADAMW_CHUNK / 4);
+  long long blocks = (n_vec + 255) / 256;
+  const long long cap = 148LL * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (check_finite)
+    (void)launch_k(grad_finite_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, g, n_vec, state4);
+  (void)launch_k(adamw_prepare_kernel, dim3(1), dim3(32), 0, st, state4, static_cast<AdamwDyn*>(dyn16), beta1, beta2, check_finite);
+  AdamwConsts k;
+  k.beta1 = beta1; k.beta2 = beta2; k.eps = eps; k.wd = wd; k.bc1 = 1.f; k.rsqrt_bc2 = 1.f;
+  k.grad_scale = grad_scale; k.lr_scale = lr_scale;
+  (void)launch_k(adamw_arena_dyn_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, p, g, m, v, chunk_lr, n_chunks, k,
+                 static_cast<const AdamwDyn*>(dyn16));
+  return check_cuda(cudaGetLastError(), "adamw_arena_dyn");
+}
+
 // ---------------------------------------------------------------- focal loss backward (layers/focal_loss.py:35-55)
 // L = -sum_{t==1} log(p)(1-p)^2 - sum_{0<=t<1} log(1-p) p^2 (1-t)^4
 // dL/dp = -( (1-p)^2 / p - 2 (1-p) log p )                          at t == 1

@@ -281,8 +281,9 @@ class DLASeg(nn.Module):
         channels-last fp16 view of the plan's output buffer; strict mode an fp32 tensor (hi + lo) that remembers its pair
         rows (`_mf_act`) so that the predictor consumes them without a conversion."""
         if self.training:
-            raise NotImplementedError("monoflex_b200 round 1 builds the inference path; the fused training path "
-                                      "(SURVEY §8 rows R5/R11-R13) is not built yet - there is no PyTorch fallback")
+            # train-mode VALUE (batch statistics); the result carries no grad_fn - gradients reach the parameters through
+            # KeypointDetector's tape bridge (model/detector.py), the training entry point
+            return self.train_forward(x)
         if not x.is_cuda:
             raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only (input is on %s); no CPU fallback" % x.device)
         x = x.float().contiguous()
@@ -292,7 +293,7 @@ class DLASeg(nn.Module):
 
     def train_forward(self, x):
         """Train-mode forward of the backbone (batch-statistics BatchNorm, running statistics updated in place) on the
-        CUDA kernels. Forward only: the backward tape is not built yet, so this is NOT reachable through forward()."""
+        CUDA kernels; records the tape `tape.backbone_backward` replays (driven by KeypointDetector's tape bridge)."""
         if not self.training:
             raise RuntimeError("train_forward needs module.train()")
         if not x.is_cuda:

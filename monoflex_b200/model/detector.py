@@ -1,6 +1,13 @@
 """KeypointDetector (reference: model/detector.py:11-37): backbone -> heads, same constructor and forward signature so
 engine/trainer.py:109 and engine/inference.py:38 call it unchanged.
 
+Training mode (engine/trainer.py:103-126): `loss_dict, log_loss_dict = model(images, targets)` runs the train-mode plans
+(batch-statistics BatchNorm, running statistics updated) and the fused loss; `sum(loss_dict.values()).backward()` then
+reaches `_TapeBridge.backward`, which replays the backward tape of the two plans (monoflex_b200/tape.py, head_backward.py)
+and ACCUMULATES the gradient of every parameter the forward used into `p.grad` - exactly what autograd does for the
+reference, so `optimizer.zero_grad(); losses.backward(); optimizer.step()` works unchanged with torch.optim.AdamW or with
+solver.FusedAdamW (whose `.grad`s are views of one arena).
+
 Eval forwards are replayed from a CUDA graph: shapes are static (384x1280 zero-padded images), so the
 ~135 kernel launches of a forward are captured once per (input shape, parameter version) and replayed with one
 cudaGraphLaunch; per call only the image batch and the per-image target fields are copied into static buffers.
@@ -16,6 +23,22 @@ from .backbone import build_backbone
 from .head.detector_head import bulid_head
 
 
+class _TapeBridge(torch.autograd.Function):
+    """Autograd boundary between the predictor outputs (fp32 `cls`, `reg`, produced by hand-written kernels outside autograd)
+    and the reference-side loss: forward hands the two maps to autograd, backward receives dL/dcls, dL/dreg and runs the
+    whole-network backward tape. `anchor` is a dummy leaf that makes autograd schedule this node."""
+
+    @staticmethod
+    def forward(ctx, anchor, cls, reg, model):
+        ctx.model = model
+        return cls.detach(), reg.detach()
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        ctx.model._tape_backward(g_cls, g_reg)
+        return None, None, None, None
+
+
 class KeypointDetector(nn.Module):
     def __init__(self, cfg):
         super(KeypointDetector, self).__init__()
@@ -25,6 +48,10 @@ class KeypointDetector(nn.Module):
         self.use_cuda_graph = os.environ.get("MF_CUDA_GRAPH", "1") != "0"
         self._graph = None
         self.set_precision(engine.default_precision())
+        # fp16 gradient flow of the backward tape: dL/dcls, dL/dreg are multiplied by `loss_scale` before they enter the
+        # tape and every parameter gradient is divided by it again before it is accumulated into p.grad (fp32)
+        self.loss_scale = float(os.environ.get("MF_LOSS_SCALE", "128"))
+        self._anchor = None
 
     def set_precision(self, mode):
         """'strict' (default): hi/lo fp16 pair arithmetic, fp32-grade results - the mode that meets the 1e-3 parity contract
@@ -41,26 +68,62 @@ class KeypointDetector(nn.Module):
             raise ValueError("In training mode, targets should be passed")
         images = to_image_list(images)
         if self.training:
-            features = self.backbone(images.tensors)
-            return self.heads(features, targets)
+            return self._forward_train(images.tensors, targets)
         x = images.tensors
         if not self.use_cuda_graph or not x.is_cuda:
             features = self.backbone(x)
             return self.heads(features, targets, test=self.test)
         return self._forward_graph(x, targets)
 
-    def train_forward_losses(self, images, targets):
-        """Train-mode FORWARD of the whole detector on the CUDA kernels: backbone and predictor with batch-statistics
-        normalisation (running statistics are updated), then Loss_Computation -> (loss_dict, log_loss_dict) like the
-        reference's training branch (model/detector.py:32-34). The losses are differentiable w.r.t. the head outputs only:
-        the layer-by-layer backward tape is not built yet, which is why forward() still raises in training mode instead of
-        returning losses whose backward() would silently stop at the predictor."""
-        if not self.training:
-            raise RuntimeError("train_forward_losses needs model.train()")
-        x = to_image_list(images).tensors
+    # ------------------------------------------------------------------ training path
+    def _forward_train(self, x, targets):
+        """model/detector.py:32-34 + detector_head.py:17-25 in training mode -> (loss_dict, log_loss_dict)."""
+        if not x.is_cuda:
+            raise RuntimeError("monoflex_b200 trains on sm_100a GPUs only; no CPU fallback")
         features = self.backbone.train_forward(x)
         pred = self.heads.predictor.train_forward(features, targets)
-        return self.heads.loss_evaluator(pred, targets)
+        if self._anchor is None or self._anchor.device != x.device:
+            self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        cls, reg = _TapeBridge.apply(self._anchor, pred['cls'], pred['reg'], self)
+        return self.heads.loss_evaluator({'cls': cls, 'reg': reg}, targets)
+
+    def train_forward_losses(self, images, targets):
+        """explicit name of the training-mode forward (kept from round 1; same as `model.train(); model(images, targets)`)"""
+        if not self.training:
+            raise RuntimeError("train_forward_losses needs model.train()")
+        return self._forward_train(to_image_list(images).tensors, targets)
+
+    @torch.no_grad()
+    def _tape_backward(self, g_cls, g_reg):
+        """dL/dcls, dL/dreg -> accumulate dL/dp into p.grad for every parameter the forward used (the backward tape)."""
+        from ..head_backward import predictor_backward
+        from ..tape import backbone_backward
+        pred_mod, S = self.heads.predictor, self.loss_scale
+        plan_h, plan_b = pred_mod.last_plan, self.backbone.last_plan
+        if g_cls is None:
+            g_cls = torch.zeros_like(plan_h.cls)
+        if g_reg is None:
+            g_reg = torch.zeros_like(plan_h.reg)
+        hgrads, d_feat = predictor_backward(pred_mod, plan_h, g_cls * S, g_reg * S)
+        bgrads = backbone_backward(self.backbone, plan_b, d_feat, stem_wgrad=True)
+        params = getattr(self, "_param_by_name", None)
+        if params is None:
+            params = self._param_by_name = dict(self.named_parameters())
+        inv = 1.0 / S
+        used = set()
+        for prefix, grads in (("heads.predictor.", hgrads), ("backbone.", bgrads)):
+            for name, g in grads.items():
+                if g is None:
+                    raise RuntimeError("backward tape produced no gradient for %s%s" % (prefix, name))
+                p = params[prefix + name]
+                used.add(prefix + name)
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = (g * inv).view_as(p)
+                else:
+                    p.grad.add_(g.view_as(p), alpha=inv)
+        self.last_grad_names = used          # parameters outside the forward graph (the reference leaves their .grad None)
 
     def forward_async(self, images, targets):
         """Enqueue one eval forward (graph replay) and return a handle; `handle.result()` waits for it and returns what

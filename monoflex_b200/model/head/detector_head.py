@@ -15,10 +15,11 @@ class Detect_Head(nn.Module):
 
     def forward(self, features, targets=None, test=False):
         if self.training:
-            # Loss_Computation itself is built (detector_loss.py); what is missing for a training step is the train-mode
-            # forward (batch-statistics BN) and the conv / DCN backward kernels - never silently run the eval kernels here
-            raise NotImplementedError("training-mode forward/backward of the backbone and predictor is a later SURVEY §8 "
-                                      "row (R5/R13); call heads.loss_evaluator(predictions, targets) directly")
+            # detector_head.py:17-21. The predictions leave the hand-written kernels outside autograd: gradients reach the
+            # parameters only through KeypointDetector's tape bridge (model/detector.py::_TapeBridge), which is why the
+            # training entry point is KeypointDetector.forward and not this sub-module on its own.
+            raise RuntimeError("Detect_Head.forward in training mode: call KeypointDetector.forward(images, targets) - the "
+                               "backward tape spans backbone and head and is attached there")
         x = self.predictor(features, targets)
         return self.post_processor(x, targets, test=test, features=features)
 

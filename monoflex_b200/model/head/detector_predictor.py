@@ -234,12 +234,11 @@ class _predictor(nn.Module):
         plan.edge_len.copy_(torch.stack([t.get_field("edge_len") for t in targets]).view(-1), non_blocking=True)
 
     def forward(self, features, targets):
-        if self.training:
-            raise NotImplementedError("training path not built yet (no PyTorch fallback)")
-        return self._run(features, targets)
+        return self._run(features, targets)      # training mode: train-mode value, see train_forward
 
     def train_forward(self, features, targets):
-        """Train-mode forward (InPlaceABN / BatchNorm1d on batch statistics). Forward only, see DLASeg.train_forward."""
+        """Train-mode forward (InPlaceABN / BatchNorm1d on batch statistics); keeps the activations
+        head_backward.predictor_backward needs (driven by KeypointDetector's tape bridge)."""
         if not self.training:
             raise RuntimeError("train_forward needs module.train()")
         return self._run(features, targets)

@@ -1,73 +1,65 @@
-"""First end-to-end training step on the CUDA kernels (reference loop: engine/trainer.py:103-126):
+"""Training step on the CUDA kernels, driven exactly like the reference loop (engine/trainer.py:103-126):
 
-    forward (train-mode plans) -> Loss_Computation -> head_backward + tape (all parameter gradients) -> gradient arena ->
-    FusedAdamW (one launch; `step_exchange()` instead when the optimiser was built with a symmetric group).
+    loss_dict, log = model(images, targets); losses = sum(loss_dict.values())
+    optimizer.zero_grad(); losses.backward(); [clip_grad_norm_]; optimizer.step(); scheduler.step()
 
-STATUS: written at the end of round 1 and NOT yet executed on hardware (the GPU budget was exhausted; every piece it calls
-is hardware-verified on its own: train-mode forward, loss, head + backbone backward tape, FusedAdamW) - its test
-(tests/test_gpu_train.py::test_end_to_end_train_steps) therefore only runs with MF_RUN_UNVERIFIED=1.
-
-This wiring is eager Python over freshly rebuilt plans (the optimiser step changes the weights, the cached plans key on the
-parameter versions, so every step re-packs the weights and re-allocates the activation buffers): it establishes CORRECTNESS
-of the whole step, not its speed - see DESIGN.md "Training tape" for the static-plan / CUDA-graph version it is a stepping
-stone to. Parameters the forward never uses (the outer `project` of the two-level trees, dla_dcn.py:249) get no gradient in
-the reference (grad None -> skipped by AdamW); here their learning rate is set to 0 after the first backward so that the
-kernel skips them too.
+`model(images, targets)` in training mode runs the train-mode plans + the fused loss; `losses.backward()` reaches the
+backward tape through `model/detector.py::_TapeBridge` and accumulates into `p.grad`. `Trainer` is that loop as an object:
+it owns the `FusedAdamW` arena optimiser, performs the data-parallel gradient exchange the reference gets from
+DistributedDataParallel (tools/plain_train_net.py:100-104: mean over ranks) - bucketed NCCL all-reduce of the gradient arena
+with the 1/world folded into the AdamW kernel, or the fused peer-memory kernel when built with `symmetric_group` - and guards
+the update with a device-side finite check of the gradient arena (fp16 gradient flow under a fixed loss scale: a non-finite
+gradient skips the step instead of poisoning params and moments; the reference trains in fp32 and stops on NaN losses,
+detector_loss.py:485-489).
 """
 import torch
+import torch.distributed as dist
 
 from . import solver
-from .head_backward import predictor_backward
-from .tape import backbone_backward
 
 
 class Trainer(object):
-    def __init__(self, model, cfg, loss_scale=128.0, symmetric_group=None):
+    def __init__(self, model, cfg, loss_scale=None, symmetric_group=None, process_group=None, bucket_bytes=32 << 20):
         if not next(model.parameters()).is_cuda:
             raise RuntimeError("monoflex_b200 trains on sm_100a GPUs only; no CPU fallback")
         self.model = model.train()
-        self.loss_scale = float(loss_scale)
+        if loss_scale is not None:
+            model.loss_scale = float(loss_scale)
+        self.cfg = cfg
+        self.group = process_group
+        self.bucket_bytes = bucket_bytes
         groups = solver.get_model_params(model, cfg)
         self.optimizer = solver.FusedAdamW(groups, lr=cfg.SOLVER.BASE_LR, weight_decay=cfg.SOLVER.WEIGHT_DECAY, betas=(0.9, 0.99),
                                            symmetric_group=symmetric_group)
-        self.params = dict(model.named_parameters())
-        self._unused_frozen = False
-        self.last_grad_names = None
+        self.scheduler, _ = solver.build_scheduler(self.optimizer, cfg.SOLVER)
+        self.grad_norm_clip = getattr(cfg.SOLVER, "GRAD_NORM_CLIP", -1)
+        self.iteration = 0
+        self._unused_marked = False
+
+    @property
+    def world(self):
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def step(self, images, targets):
         """one optimisation step on a batch -> (loss_dict, log_loss_dict) of the forward that produced the gradients"""
-        model, S = self.model, self.loss_scale
+        model, opt = self.model, self.optimizer
         model.train()
-        feats = model.backbone.train_forward(images)
-        pred_mod = model.heads.predictor
-        pred = pred_mod.train_forward(feats, targets)
-        c = pred["cls"].detach().clone().requires_grad_(True)
-        r = pred["reg"].detach().clone().requires_grad_(True)
-        loss_dict, log = model.heads.loss_evaluator({"cls": c, "reg": r}, targets)
-        (S * sum(loss_dict.values())).backward()                              # fused loss backward -> d cls, d reg
-        hgrads, d_feat = predictor_backward(pred_mod, pred_mod.last_plan, c.grad, r.grad)
-        bgrads = backbone_backward(model.backbone, model.backbone.last_plan, d_feat, stem_wgrad=True)
-        self.optimizer.zero_grad()
-        got = set()
-        with torch.no_grad():
-            for prefix, grads in (("heads.predictor.", hgrads), ("backbone.", bgrads)):
-                for name, g in grads.items():
-                    if g is None:
-                        raise RuntimeError("no gradient was produced for %s%s" % (prefix, name))
-                    self.params[prefix + name].grad.copy_(g)                  # .grad is a view of the optimiser's arena
-                    got.add(prefix + name)
-        self.last_grad_names = got
-        if not self._unused_frozen:                                           # parameters outside the forward graph: lr 0
-            for group in self.optimizer.param_groups:
-                p = group["params"][0]
-                if not any(p is self.params[n] for n in got):
-                    group["lr"] = 0.0
-                    group["initial_lr"] = 0.0
-            self._unused_frozen = True
-        if self.optimizer._symm is not None:
-            # the fused exchange kernel scales the reduced gradient by 1/world only: remove the loss scale first (one launch)
-            self.optimizer.arena.grads.mul_(1.0 / S)
-            self.optimizer.step_exchange()
+        loss_dict, log = model(images, targets)
+        losses = sum(loss_dict.values())
+        opt.zero_grad()
+        losses.backward()                                            # fused loss backward -> tape bridge -> p.grad (arena views)
+        if not self._unused_marked:                                  # parameters outside the forward graph: the reference's
+            opt.mark_unused({n for n, _ in model.named_parameters()} - set(model.last_grad_names), model)   # AdamW skips grad None
+            self._unused_marked = True
+        if self.grad_norm_clip > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), self.grad_norm_clip)
+        world = self.world
+        if opt._symm is not None:
+            opt.step_exchange()                                      # reduce + AdamW + broadcast in one peer-memory kernel
         else:
-            self.optimizer.step(grad_scale=1.0 / S)
+            if world > 1:
+                solver.allreduce_grads(opt.arena, self.bucket_bytes, self.group)
+            opt.step(grad_scale=1.0 / world)
+        self.scheduler.step()
+        self.iteration += 1
         return {k: v.detach() for k, v in loss_dict.items()}, log
