@@ -83,6 +83,14 @@ int mf_conv2d_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W,
 int mf_dcn_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const float* offmask, int om_ld,
                       const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
                       void* y, int y_ld, int y_lo, void* stream);
+/* Row-segment stem kernel (mf_conv2d_rows_f16) on pairs. in_mode 1 (Cin = 8): x is the image pair plane [hi3 | lo3 | 0 0]
+ * (mf_pack_image_pair8) and w_packed holds TWO tap sets stacked along ky ([W_hi | W_hi | 0 0] then [W_lo | 0 ...], kw padded
+ * to 8); in_mode 2 (Cin = 16, stride 1): x = pair planes [hi0 hi1 lo0 lo1], w_packed = THREE stacked tap sets (W_hi, W_hi,
+ * W_lo). Output always a pair: planar (hi planes then lo planes) or NHWC rows with the lo block y_lo elements after hi. */
+int mf_conv2d_rows_f16x2(const void* x, int B, int H, int W, int Cin, int in_npar, int in_mode, const void* w_packed, int n_pad,
+                         int k_pad, int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
+                         int out_planar, int out_npar, void* y, int y_ld, int y_lo, void* stream);
+int mf_pack_image_pair8(const float* x_nchw, void* y_nhwc8, int B, int C, int H, int W, void* stream);
 /* image [B,3,H,W] fp32 -> [B*H*W, 16] fp16 rows [hi3 | lo3 | hi3 | 0 x 7] (the stem then is a plain 16-channel conv with
  * per-tap weights [W_hi | W_hi | W_lo | 0]) */
 int mf_pack_image_split(const float* x_nchw, void* y_rows16, int B, int C, int H, int W, void* stream);
@@ -274,6 +282,18 @@ int mf_adamw_step_p2p(const unsigned long long* param_ptrs, const unsigned long 
 int mf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* chunk_lr,
                   long long n_chunks, float beta1, float beta2, float eps, float weight_decay, long long step,
                   float grad_scale, float lr_scale, void* stream);
+
+/* ---- GPU input pipeline. mf_preprocess_images_u8: B uint8 HWC RGB images of individual sizes h x w <= H x W
+ * (src_ptrs: DEVICE array of B device pointers; hw4: DEVICE int32 [B][4] = h, w, pad_x, pad_y with pad = (W - w) / 2, (H - h) / 2
+ * as in KITTIDataset.pad_image, data/datasets/kitti.py:218-228; flip: DEVICE int32 [B] or NULL, horizontal flip of the un-padded
+ * image) -> zero padding on the uint8 image, x / 255 (ToTensor), (x - mean) / std (Normalize, data/transforms/transforms.py:14-30,
+ * IEEE divisions: bit-identical to torch), optional RGB->BGR -> fp32 NCHW [B,3,H,W] = the detector's input. mean3 / std3: HOST.
+ * mf_draw_heatmaps: obj6 DEVICE int32 [B][max_objs][6] = valid, class, cx, cy, rx, ry -> hm fp32 [B][ncls][H][W], element-wise
+ * max of the objects' Gaussians (model/heatmap_coder.py:56-64, 83-124: rx == ry draw_umich_gaussian, else the one-sided
+ * draw_umich_gaussian_2D), sigma = (2 r + 1) / 6, double arithmetic rounded to fp32 like numpy. */
+int mf_preprocess_images_u8(const void* const* src_ptrs, const int* hw4, const int* flip, int B, int H, int W,
+                            const float* mean3, const float* std3, int to_bgr, float* out_nchw, void* stream);
+int mf_draw_heatmaps(const int* obj6, int B, int max_objs, int ncls, int H, int W, float* hm, void* stream);
 
 /* nms_hm alone (model/layers/utils.py:45-58): out = heat * (maxpool3x3(heat) == heat), planes = B*C */
 int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream);

@@ -183,6 +183,17 @@ int mf_conv2d_rows_f16(const void* x, int B, int H, int W, int Cin, int in_npar,
                           y_ld, MF_STREAM(stream));
 }
 
+int mf_conv2d_rows_f16x2(const void* x, int B, int H, int W, int Cin, int in_npar, int in_mode, const void* w_packed, int n_pad,
+                         int k_pad, int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
+                         int out_planar, int out_npar, void* y, int y_ld, int y_lo, void* stream) {
+  return launch_rows_conv(static_cast<const __half*>(x), B, H, W, Cin, in_npar, static_cast<const __half*>(w_packed), n_pad,
+                          k_pad, kh, kw, stride, pad, Cout, scale, shift, act, out_planar, out_npar, static_cast<__half*>(y),
+                          y_ld, MF_STREAM(stream), in_mode, 1, y_lo);
+}
+int mf_pack_image_pair8(const float* x_nchw, void* y_nhwc8, int B, int C, int H, int W, void* stream) {
+  return launch_pack_image_pair8(x_nchw, static_cast<__half*>(y_nhwc8), B, C, H, W, MF_STREAM(stream));
+}
+
 int mf_head_fused(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w3_packed, const void* w2_packed,
                   const float* scale, const float* shift, const float* bias2, int nbranch, void* const* out_ptrs,
                   const int* out_ctot, const int* out_nch, const int* hid_col, void* hid, int hid_ld,
@@ -359,6 +370,14 @@ int mf_adamw_step_p2p(const unsigned long long* param_ptrs, const unsigned long 
                       long long step, float lr_scale, void* stream) {
   return launch_adamw_p2p(param_ptrs, grad_ptrs, world, rank, mc_params, mc_grads, exp_avg, exp_avg_sq, chunk_lr, n_chunks,
                           beta1, beta2, eps, weight_decay, step, lr_scale, MF_STREAM(stream));
+}
+int mf_preprocess_images_u8(const void* const* src_ptrs, const int* hw4, const int* flip, int B, int H, int W,
+                            const float* mean3, const float* std3, int to_bgr, float* out_nchw, void* stream) {
+  return launch_preprocess_u8(reinterpret_cast<const unsigned char* const*>(src_ptrs), hw4, flip, B, H, W, mean3, std3, to_bgr,
+                              out_nchw, MF_STREAM(stream));
+}
+int mf_draw_heatmaps(const int* obj6, int B, int max_objs, int ncls, int H, int W, float* hm, void* stream) {
+  return launch_draw_heatmap(obj6, B, max_objs, ncls, H, W, hm, MF_STREAM(stream));
 }
 int mf_nms_hm(const float* heat, float* out, int planes, int H, int W, void* stream) {
   return launch_nms_hm(heat, out, planes, H, W, MF_STREAM(stream));

@@ -55,21 +55,39 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const __half* __restric
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
   if (r < RL) {
-    for (long long row = r0 + r; row < r1; row += RL) {
-      float xv[8];
-      bn_unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * x_ld + cv * 8)), xv);
-      if (!BWD) {
+    constexpr int U = 4;                                   // rows in flight per thread: all loads of a group are issued first
+    for (long long row = r0 + r; row < r1; row += static_cast<long long>(U) * RL) {
+      uint4 xq[U], gq[U], yq[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a[e] += xv[e]; b[e] += xv[e] * xv[e]; }
-      } else {
-        float gv[8], yv[8];
-        bn_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * dy_ld + cv * 8)), gv);
-        bn_unpack8(__ldg(reinterpret_cast<const uint4*>(y + row * y_ld + cv * 8)), yv);
+      for (int u = 0; u < U; ++u) {
+        const long long rr = row + static_cast<long long>(u) * RL;
+        const bool ok = rr < r1;
+        const long long rc = ok ? rr : row;
+        xq[u] = __ldg(reinterpret_cast<const uint4*>(x + rc * x_ld + cv * 8));
+        if (BWD) {
+          gq[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + rc * dy_ld + cv * 8)) : make_uint4(0u, 0u, 0u, 0u);
+          yq[u] = __ldg(reinterpret_cast<const uint4*>(y + rc * y_ld + cv * 8));
+        } else if (!ok) {
+          xq[u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float g = gv[e] * bn_act_grad(yv[e], act);
-          a[e] += g;
-          b[e] += g * (xv[e] - mu[e]) * rs[e];
+      for (int u = 0; u < U; ++u) {                        // fixed accumulation order: row, row + RL, ...
+        float xv[8];
+        bn_unpack8(xq[u], xv);
+        if (!BWD) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { a[e] += xv[e]; b[e] += xv[e] * xv[e]; }
+        } else {
+          float gv[8], yv[8];
+          bn_unpack8(gq[u], gv);
+          bn_unpack8(yq[u], yv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g = gv[e] * bn_act_grad(yv[e], act);
+            a[e] += g;
+            b[e] += g * (xv[e] - mu[e]) * rs[e];
+          }
         }
       }
     }
@@ -84,16 +102,25 @@ __global__ void __launch_bounds__(256) bn_partial_kernel(const __half* __restric
   }
 }
 
-// forward finalize: one thread per channel
+// fixed-order double sum of part[k][which][c], k < ncta, by one warp: lane l takes k = l, l + 32, ... then a shuffle tree
+MF_DEVINL double bn_warp_sum(const float* __restrict__ part, int ncta, int C, int which, int c, int lane) {
+  double s = 0.0;
+  for (int k = lane; k < ncta; k += 32) s += static_cast<double>(part[(static_cast<long long>(k) * 2 + which) * C + c]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  return s;
+}
+
+// forward finalize: one WARP per channel (a single thread walking ~1000 partials was 22 us of pure latency per layer)
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int ncta, int C, long long M, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, int abs_gamma,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
                                    float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < ncta; ++k) { s += part[(static_cast<long long>(k) * 2 + 0) * C + c]; ss += part[(static_cast<long long>(k) * 2 + 1) * C + c]; }
+  const double s = bn_warp_sum(part, ncta, C, 0, c, lane), ss = bn_warp_sum(part, ncta, C, 1, c, lane);
+  if (lane != 0) return;
   const double mean = s / static_cast<double>(M);
   double var = ss / static_cast<double>(M) - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -120,12 +147,18 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict_
   if (i >= M * CV) return;
   const int cv = static_cast<int>(i % CV);
   const long long row = i / CV;
-  float v[8], rv[8];
-  bn_unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * x_ld + cv * 8)), v);
-  if (res != nullptr) bn_unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * res_ld + cv * 8)), rv);
+  float v[8], rv[8], sc[8], sh[8];
+  const uint4 xq = __ldg(reinterpret_cast<const uint4*>(x + row * x_ld + cv * 8));
+  const uint4 rq = res != nullptr ? __ldg(reinterpret_cast<const uint4*>(res + row * res_ld + cv * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<float4*>(&sc[0]) = __ldg(reinterpret_cast<const float4*>(scale + cv * 8));
+  *reinterpret_cast<float4*>(&sc[4]) = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
+  *reinterpret_cast<float4*>(&sh[0]) = __ldg(reinterpret_cast<const float4*>(shift + cv * 8));
+  *reinterpret_cast<float4*>(&sh[4]) = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
+  bn_unpack8(xq, v);
+  bn_unpack8(rq, rv);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    float t = v[e] * __ldg(scale + cv * 8 + e) + __ldg(shift + cv * 8 + e);
+    float t = v[e] * sc[e] + sh[e];
     if (res != nullptr) t += rv[e];
     if (act == 1) t = fmaxf(t, 0.f);
     else if (act == 2) t = fmaxf(t, 0.01f * t);
@@ -136,10 +169,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict_
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int ncta, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ sum_g, float* __restrict__ sum_gx) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int k = 0; k < ncta; ++k) { s += part[(static_cast<long long>(k) * 2 + 0) * C + c]; sx += part[(static_cast<long long>(k) * 2 + 1) * C + c]; }
+  const double s = bn_warp_sum(part, ncta, C, 0, c, lane), sx = bn_warp_sum(part, ncta, C, 1, c, lane);
+  if (lane != 0) return;
   dbeta[c] = static_cast<float>(s);
   dgamma[c] = static_cast<float>(sx);
   sum_g[c] = static_cast<float>(s);
@@ -159,17 +192,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
   if (i >= M * CV) return;
   const int cv = static_cast<int>(i % CV);
   const long long row = i / CV;
-  float xv[8], gv[8], yv[8], o[8], gr[8];
-  bn_unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * x_ld + cv * 8)), xv);
-  bn_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * dy_ld + cv * 8)), gv);
-  bn_unpack8(__ldg(reinterpret_cast<const uint4*>(y + row * y_ld + cv * 8)), yv);
+  float xv[8], gv[8], yv[8], o[8], gr[8], mu[8], rs[8], sc[8], sg[8], sgx[8];
+  const uint4 xq = __ldg(reinterpret_cast<const uint4*>(x + row * x_ld + cv * 8));
+  const uint4 gq = __ldg(reinterpret_cast<const uint4*>(dy + row * dy_ld + cv * 8));
+  const uint4 yq = __ldg(reinterpret_cast<const uint4*>(y + row * y_ld + cv * 8));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    *reinterpret_cast<float4*>(&mu[4 * h]) = __ldg(reinterpret_cast<const float4*>(mean + cv * 8 + 4 * h));
+    *reinterpret_cast<float4*>(&rs[4 * h]) = __ldg(reinterpret_cast<const float4*>(rstd + cv * 8 + 4 * h));
+    *reinterpret_cast<float4*>(&sc[4 * h]) = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4 * h));
+    *reinterpret_cast<float4*>(&sg[4 * h]) = __ldg(reinterpret_cast<const float4*>(sum_g + cv * 8 + 4 * h));
+    *reinterpret_cast<float4*>(&sgx[4 * h]) = __ldg(reinterpret_cast<const float4*>(sum_gx + cv * 8 + 4 * h));
+  }
+  bn_unpack8(xq, xv);
+  bn_unpack8(gq, gv);
+  bn_unpack8(yq, yv);
   const float inv_m = 1.f / static_cast<float>(M);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = cv * 8 + e;
     const float g = gv[e] * bn_act_grad(yv[e], act);
-    const float xhat = (xv[e] - __ldg(mean + c)) * __ldg(rstd + c);
-    o[e] = __ldg(scale + c) * (g - __ldg(sum_g + c) * inv_m - xhat * __ldg(sum_gx + c) * inv_m);
+    const float xhat = (xv[e] - mu[e]) * rs[e];
+    o[e] = sc[e] * (g - sg[e] * inv_m - xhat * sgx[e] * inv_m);
     gr[e] = g;
   }
   *reinterpret_cast<uint4*>(dx + row * dx_ld + cv * 8) = bn_pack8(o);
@@ -213,7 +256,7 @@ int launch_bn_train_forward(const __half* x, int x_ld, long long M, int C, const
   (void)launch_k(bn_partial_kernel<false>, dim3(ncta), dim3(th), sm, st, x, x_ld, static_cast<const __half*>(nullptr), 0,
                  static_cast<const __half*>(nullptr), 0, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), M,
                  C, 0, rpc, workspace);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, ncta, C, M, gamma, beta, eps, momentum, abs_gamma, running_mean,
+  bn_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(workspace, ncta, C, M, gamma, beta, eps, momentum, abs_gamma, running_mean,
                                                       running_var, mean, rstd, scale, shift);
   const long long n = M * (C / 8);
   (void)launch_k(bn_apply_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, x_ld,
@@ -234,7 +277,7 @@ int launch_bn_train_backward(const __half* x, int x_ld, const __half* dy, int dy
   float* sums = workspace + static_cast<size_t>(ncta) * 2 * C;        // [2][C] after the partials
   (void)launch_k(bn_partial_kernel<true>, dim3(ncta), dim3(th), sm, st, x, x_ld, dy, dy_ld, y, y_ld, mean, rstd, M, C, act, rpc,
                  workspace);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, ncta, C, dgamma, dbeta, sums, sums + C);
+  bn_bwd_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(workspace, ncta, C, dgamma, dbeta, sums, sums + C);
   const long long n = M * (C / 8);
   (void)launch_k(bn_bwd_apply_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, x_ld, dy, dy_ld, y, y_ld,
                  mean, rstd, scale, static_cast<const float*>(sums), static_cast<const float*>(sums + C), act, dx, dx_ld, dres,

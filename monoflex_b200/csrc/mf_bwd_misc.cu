@@ -299,40 +299,82 @@ int launch_edge_gather_bwd(const __half* d_ea, const __half* d_eb, int ch_a, int
 // forward: out[b, ch0 + o, ey, ex] += bias[o] + sum_c t[b, e, c] * w[o, c] for the first edge_len[b] border positions e.
 // backward: d_t[b, e, c] = sum_o g[o] w[o, c] (0 past edge_len), dw[o, c] += g[o] t[b, e, c], dbias[o] += g[o], with
 // g[o] = d_out[b, ch0 + o, ey, ex]. One warp per (b, e); dw / dbias by fp32 atomics (zeroed by the launcher).
-__global__ void edge_head_add_bwd_kernel(const __half* __restrict__ t, const float* __restrict__ w, int n_out,
+template <int NO>
+__global__ void __launch_bounds__(256) edge_head_add_bwd_kernel(const __half* __restrict__ t, const float* __restrict__ w, int n_out,
                                          const long long* __restrict__ edge_idx, const long long* __restrict__ edge_len,
                                          const float* __restrict__ d_out, int out_ctot, int out_ch0, __half* __restrict__ d_t,
                                          float* __restrict__ dw, float* __restrict__ dbias, int B, int K, int H, int W) {
+  // 8 warps per CTA, each walking EDGE_PER_WARP consecutive (b, e) positions: the weight / bias gradients are summed in
+  // registers, then across the CTA's warps in shared memory, and only one atomic per (o, c) per CTA reaches `dw` (the
+  // first version issued one per position: ~6.6 k warps hammering the same 768 addresses, 0.9 ms per launch).
   pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * K) return;
-  const int b = warp / K, e = warp - b * K;
-  float acc[8];
+  constexpr int EDGE_PER_WARP = 8;
+  __shared__ float red[8][NO][256 + 1];
+  __shared__ float redb[8][NO];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dwa[NO][8], dba[NO];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  if (e < edge_len[b]) {
-    float tv[8];
-    bm_unpack8(__ldg(reinterpret_cast<const uint4*>(t + static_cast<long long>(warp) * 256 + lane * 8)), tv);
-    const long long ex = edge_idx[(static_cast<long long>(b) * K + e) * 2], ey = edge_idx[(static_cast<long long>(b) * K + e) * 2 + 1];
-    for (int o = 0; o < n_out; ++o) {
-      const float g = __ldg(d_out + ((static_cast<long long>(b) * out_ctot + out_ch0 + o) * H + ey) * W + ex);
+  for (int o = 0; o < NO; ++o) {
+    dba[o] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        acc[q] += g * __ldg(w + o * 256 + lane * 8 + q);
-        atomicAdd(dw + o * 256 + lane * 8 + q, g * tv[q]);
-      }
-      if (lane == 0) atomicAdd(dbias + o, g);
-    }
+    for (int q = 0; q < 8; ++q) dwa[o][q] = 0.f;
   }
-  *reinterpret_cast<uint4*>(d_t + static_cast<long long>(warp) * 256 + lane * 8) = bm_pack8(acc);
+  const int first = (blockIdx.x * 8 + wib) * EDGE_PER_WARP;
+  for (int i = 0; i < EDGE_PER_WARP; ++i) {
+    const int pos = first + i;
+    if (pos >= B * K) break;
+    const int b = pos / K, e = pos - b * K;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    if (e < edge_len[b]) {
+      float tv[8];
+      bm_unpack8(__ldg(reinterpret_cast<const uint4*>(t + static_cast<long long>(pos) * 256 + lane * 8)), tv);
+      const long long ex = edge_idx[(static_cast<long long>(b) * K + e) * 2], ey = edge_idx[(static_cast<long long>(b) * K + e) * 2 + 1];
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        if (o < n_out) {
+          const float g = __ldg(d_out + ((static_cast<long long>(b) * out_ctot + out_ch0 + o) * H + ey) * W + ex);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            acc[q] += g * __ldg(w + o * 256 + lane * 8 + q);
+            dwa[o][q] += g * tv[q];
+          }
+          dba[o] += g;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(d_t + static_cast<long long>(pos) * 256 + lane * 8) = bm_pack8(acc);
+  }
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[wib][o][lane * 8 + q] = dwa[o][q];
+    if (lane == 0) redb[wib][o] = dba[o];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_out * 256; i += blockDim.x) {
+    const int o = i >> 8, c = i & 255;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][o][c];
+    if (s != 0.f) atomicAdd(dw + o * 256 + c, s);
+  }
+  if (threadIdx.x < n_out) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += redb[k][threadIdx.x];
+    if (s != 0.f) atomicAdd(dbias + threadIdx.x, s);
+  }
 }
 int launch_edge_head_add_bwd(const __half* t, const float* w, int n_out, const long long* edge_idx, const long long* edge_len,
                              const float* d_out, int out_ctot, int out_ch0, __half* d_t, float* dw, float* dbias, int B, int K,
                              int H, int W, cudaStream_t st) {
   if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * 256, st), "edge_head_add_bwd memset")) return -1;
   if (check_cuda(cudaMemsetAsync(dbias, 0, sizeof(float) * n_out, st), "edge_head_add_bwd memset")) return -1;
-  const long long threads = static_cast<long long>(B) * K * 32;
-  (void)launch_k(edge_head_add_bwd_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, t, w, n_out,
+  if (n_out < 1 || n_out > 4) { set_error("edge_head_add_bwd: n_out %d (1..4 supported)", n_out); return -1; }
+  const int blocks = (B * K + 63) / 64;                          // 8 warps x 8 positions per CTA
+  (void)launch_k(edge_head_add_bwd_kernel<4>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, t, w, n_out,
                  edge_idx, edge_len, d_out, out_ctot, out_ch0, d_t, dw, dbias, B, K, H, W);
   return check_cuda(cudaGetLastError(), "edge_head_add_bwd");
 }

@@ -43,6 +43,12 @@ MF_DEVINL DcnRec dcn_rec(const float* __restrict__ om, int H, int W, int y, int 
   if (bt && rt) { r.w[3] = lh * lw; r.dh[3] = lw; r.dw[3] = lh; }
   return r;
 }
+// red.global.add.noftz.v4.f16x2 (sm_90+): 8 fp16 additions to 16 contiguous, 16-byte aligned bytes as ONE L2 reduction request
+MF_DEVINL void red_add_v4_f16x2(__half* addr, const __half2 (&v)[4]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3])
+               : "memory");
+}
 MF_DEVINL void dcn_unpack8(const uint4& v, float (&f)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -124,9 +130,12 @@ __global__ void __launch_bounds__(256) dcn_col2im_kernel(const __half* __restric
         for (int e = 0; e < 8; ++e) { val[e] += r.w[q] * v[e]; vh[e] += r.dh[q] * v[e]; vw[e] += r.dw[q] * v[e]; }
         if (r.w[q] != 0.f) {
           const float wq = r.w[q] * r.mask;
-          __half2* dst = reinterpret_cast<__half2*>(dxb + static_cast<long long>(r.idx[q]) * dx_ld + cv * 8);
+          // ONE 16-byte vector reduction per (corner, 8 channels) instead of four half2 atomics: the 2.6 G half2 atomics of a
+          // B = 8 step ran AT the L2 atomic request rate (~220 G/s, 11.8 ms); the vector form is one L2 request
+          __half2 hv[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) atomicAdd(dst + h, __floats2half2_rn(g[2 * h] * wq, g[2 * h + 1] * wq));
+          for (int h = 0; h < 4; ++h) hv[h] = __floats2half2_rn(g[2 * h] * wq, g[2 * h + 1] * wq);
+          red_add_v4_f16x2(dxb + static_cast<long long>(r.idx[q]) * dx_ld + cv * 8, hv);
         }
       }
 #pragma unroll

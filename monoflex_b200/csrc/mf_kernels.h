@@ -43,10 +43,13 @@ struct IgemmParams {
 };
 
 int igemm_block_n(int cout);
+int launch_conv_wgrad_narrow(const __half* x, int x_ld, int B, int H, int W, const __half* dy, int dy_ld, int k, float* dw,
+                             cudaStream_t st);
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar, const __half* wp, int n_pad, int k_pad,
                      int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
-                     int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st);
+                     int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st, int in_mode = 0, int split_out = 0,
+                     int y_lo = 0);
 int launch_head_fused(const __half* x, int x_ld, int B, int H, int W, int Cin, const __half* w3, const __half* w2,
                       const float* scale, const float* shift, const float* bias2, int nbranch, float* const* out,
                       const int* out_ctot, const int* out_nch, const int* hid_col, __half* hid, int hid_ld,

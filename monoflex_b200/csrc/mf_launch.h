@@ -77,9 +77,14 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
 int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                             __half* out, cudaStream_t st);
+// GPU input pipeline (mf_input.cu)
+int launch_preprocess_u8(const unsigned char* const* src, const int* hw, const int* flip, int B, int H, int W,
+                         const float* mean3, const float* std3, int to_bgr, float* out, cudaStream_t st);
+int launch_draw_heatmap(const int* obj, int B, int max_objs, int ncls, int H, int W, float* hm, cudaStream_t st);
 // strict-precision (hi/lo fp16 pairs) companions, mf_split.cu
 int launch_pack_conv_weight_split(const float* w, int Cout, int Cin, int kh, int kw, int n_pad, int k_pad, __half* out,
                                   cudaStream_t st);
+int launch_pack_image_pair8(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st);
 int launch_pack_image_split(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st);
 int launch_maxpool2_split(const __half* x, int x_lo, __half* y, int y_lo, int B, int H, int W, int C, int x_ld, int y_ld,
                           cudaStream_t st);

@@ -24,12 +24,13 @@ static constexpr int SEG_PIX = 136;
 static constexpr int SEG_BYTES = SEG_PIX * 16;     // 2176 = 17 * 128
 static constexpr int R_STAGES = 6;
 static constexpr int MAX_SEG = 12;
-static constexpr int MAX_MMA = 28;
+static constexpr int MAX_MMA = 56;          // strict precision: 2 x 28 (image pair plane) or 3 x 9 (pair planes) products
 
 struct RowsParams {
   int B, H, Gin, Wg_in;          // input planes [B][H][Gin][Wg_in][8]
   int Ho, Wo, stride, pad;
   int nseg, nmma, nkb;           // nkb = k_pad / 64 weight K blocks
+  int nstages;                   // row-segment ring depth (<= R_STAGES), sized on the host so that two CTAs fit one SM
   int seg_g[MAX_SEG], seg_dy[MAX_SEG], seg_dx[MAX_SEG];      // group, input row = oy*stride + dy, start index = ox0 + dx
   int mma_a[MAX_MMA], mma_lbo[MAX_MMA], mma_b[MAX_MMA];      // byte offsets: A start within the stage, LBO, B start
   int Cout;
@@ -40,6 +41,8 @@ struct RowsParams {
   int out_npar;
   __half* y;
   int y_ld;
+  int split_out;                 // strict precision: output = fp16 pair (hi planes then lo planes / lo block y_lo after hi)
+  int y_lo;
 };
 
 MF_DEVINL void tma_load_5d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
@@ -61,7 +64,8 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int stage_stride = (stage_bytes + 1023) & ~1023;
   uint8_t* b_smem = smem;                                     // [nkb][BLOCK_N][128 B] swizzled weight blocks
   uint8_t* a_smem = smem + ((p.nkb * BLOCK_N * 128 + 1023) & ~1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_smem + R_STAGES * stage_stride);
+  const int NST = p.nstages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(a_smem + NST * stage_stride);
   uint64_t* empty_bar = full_bar + R_STAGES;
   uint64_t* acc_full = empty_bar + R_STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -77,7 +81,7 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < R_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
@@ -107,7 +111,7 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int sgi = 0; sgi < p.nseg; ++sgi)
           tma_load_5d(dst + sgi * SEG_BYTES, &tmap_x, &full_bar[stage], 0, ox0 + p.seg_dx[sgi], p.seg_g[sgi],
                       oy * p.stride + p.seg_dy[sgi], b);
-        if (++stage == R_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -137,7 +141,7 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           umma_f16(d_tmem, desc_tab[2 * i] + a_off, desc_tab[2 * i + 1], idesc, i != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full[acc]);
-        if (++stage == R_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -164,30 +168,37 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (ox >= p.Wo) continue;
-      __half2 o[BLOCK_N / 2];
+      __half2 o[BLOCK_N / 2], ol[BLOCK_N / 2];
 #pragma unroll
       for (int i = 0; i < BLOCK_N; i += 2) {
         float f0 = __uint_as_float(v[i]) * sc[i] + sh[i];
         float f1 = __uint_as_float(v[i + 1]) * sc[i + 1] + sh[i + 1];
         if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
         o[i / 2] = __floats2half2_rn(f0, f1);
+        const float2 hf = __half22float2(o[i / 2]);
+        ol[i / 2] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);          // lo half of the pair (dead code unless split_out)
       }
       if (p.out_planar) {
         const int npar = p.out_npar, Wg = p.Wo / npar;
         const int par = npar == 2 ? (ox & 1) : 0, xi = npar == 2 ? (ox >> 1) : ox;
-        const int G = (p.Cout / 8) * npar;
+        const int Ghalf = (p.Cout / 8) * npar, G = p.split_out ? 2 * Ghalf : Ghalf;
 #pragma unroll
         for (int pl = 0; pl < BLOCK_N / 8; ++pl) {
           if (pl * 8 < p.Cout) {
             __half* dst = p.y + ((static_cast<long long>(b * p.Ho + oy) * G + (pl * npar + par)) * Wg + xi) * 8;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&o[pl * 4]);
+            if (p.split_out)
+              *reinterpret_cast<uint4*>(dst + static_cast<long long>(Ghalf) * Wg * 8) = *reinterpret_cast<const uint4*>(&ol[pl * 4]);
           }
         }
       } else {
         __half* dst = p.y + (static_cast<long long>(b * p.Ho + oy) * p.Wo + ox) * p.y_ld;
 #pragma unroll
         for (int pl = 0; pl < BLOCK_N / 8; ++pl)
-          if (pl * 8 < p.Cout) *reinterpret_cast<uint4*>(dst + pl * 8) = *reinterpret_cast<const uint4*>(&o[pl * 4]);
+          if (pl * 8 < p.Cout) {
+            *reinterpret_cast<uint4*>(dst + pl * 8) = *reinterpret_cast<const uint4*>(&o[pl * 4]);
+            if (p.split_out) *reinterpret_cast<uint4*>(dst + p.y_lo + pl * 8) = *reinterpret_cast<const uint4*>(&ol[pl * 4]);
+          }
       }
     }
   }
@@ -218,14 +229,28 @@ static PFN_encodeTiledR rows_encode_fn() {
 
 // x: planes [B][H][Gin][Wg_in][8] fp16 with Gin = (Cin/8) * in_npar; wp: packed weights [n_pad, k_pad] fp16 whose K order is
 // (ky, kx, c) with c over Cin (Cin = 16) or (ky, kx over kw_pad = 8, c over 8) (Cin = 8).
+// in_mode 0: plain fp16 planes. Strict precision (fp16 pairs):
+//   in_mode 1 (Cin = 8): the image pair plane [hi3 | lo3 | 0 0]; weights packed as TWO tap sets stacked along ky,
+//              [W_hi | W_hi | 0 0] (A_hi W_hi + A_lo W_hi in one K = 8 slot) and [W_lo | 0 ...] (A_hi W_lo);
+//   in_mode 2 (Cin = 16): pair planes [hi0 hi1 lo0 lo1]; weights packed as THREE tap sets stacked along ky:
+//              W_hi (x hi planes), W_hi (x lo planes), W_lo (x hi planes).
+// The extra products are extra entries of the MMA table over the SAME resident row segments - no extra loads for in_mode 1.
 int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar, const __half* wp, int n_pad, int k_pad,
                      int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
-                     int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st) {
+                     int out_planar, int out_npar, __half* y, int y_ld, cudaStream_t st, int in_mode, int split_out,
+                     int y_lo) {
   PFN_encodeTiledR enc = rows_encode_fn();
   if (!enc) return -1;
   RowsParams p;
   memset(&p, 0, sizeof(p));
   const int P = Cin / 8;
+  const int nsets = in_mode == 1 ? 2 : (in_mode == 2 ? 3 : 1);
+  const int Ptot = in_mode == 2 ? 2 * P : P;             // planes in memory (hi planes, then lo planes)
+  if (in_mode < 0 || in_mode > 2 || (in_mode == 1 && Cin != 8) || (in_mode == 2 && (Cin != 16 || stride != 1)) ||
+      (split_out && !out_planar && y_lo % 8 != 0)) {
+    set_error("rows_conv: unsupported strict-precision configuration (in_mode %d, Cin %d, stride %d)", in_mode, Cin, stride);
+    return -1;
+  }
   if ((Cin != 8 && Cin != 16) || (stride != 1 && stride != 2) || (stride == 2 && (in_npar != 2 || kw != 3 || pad != 1)) ||
       (stride == 1 && in_npar != 1) || (n_pad != 16 && n_pad != 32) || k_pad % 64 != 0 || W % in_npar != 0 ||
       (Cin == 8 && kw > 8) || pad > 3 || kw - 1 - pad > 4) {
@@ -233,7 +258,8 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
               kw, pad, n_pad);
     return -1;
   }
-  p.B = B; p.H = H; p.Gin = P * in_npar; p.Wg_in = W / in_npar;
+  p.B = B; p.H = H; p.Gin = Ptot * in_npar; p.Wg_in = W / in_npar;
+  p.split_out = split_out; p.y_lo = y_lo;
   p.Ho = (H + 2 * pad - kh) / stride + 1;
   p.Wo = (W + 2 * pad - kw) / stride + 1;
   p.stride = stride; p.pad = pad; p.nkb = k_pad / 64;
@@ -242,9 +268,9 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
   if (out_planar && (Cout % 8 != 0 || p.Wo % out_npar != 0)) { set_error("rows_conv: planar output needs Cout %% 8 == 0"); return -1; }
   // ---- segments and MMA table
   int nseg = 0, nmma = 0;
-  auto seg_index = [&](int ky, int plane, int par) { return (ky * P + plane) * (stride == 2 ? 2 : 1) + par; };
+  auto seg_index = [&](int ky, int plane, int par) { return (ky * Ptot + plane) * (stride == 2 ? 2 : 1) + par; };
   for (int ky = 0; ky < kh; ++ky)
-    for (int plane = 0; plane < P; ++plane)
+    for (int plane = 0; plane < Ptot; ++plane)
       for (int par = 0; par < (stride == 2 ? 2 : 1); ++par) {
         if (nseg >= MAX_SEG) { set_error("rows_conv: too many segments"); return -1; }
         p.seg_g[nseg] = plane * in_npar + par;
@@ -253,25 +279,28 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
         ++nseg;
       }
   const int kw_pad = Cin == 8 ? 8 : kw;
-  if (k_pad < kh * kw_pad * Cin) { set_error("rows_conv: k_pad too small"); return -1; }
+  if (k_pad < nsets * kh * kw_pad * Cin) { set_error("rows_conv: k_pad too small"); return -1; }
+  for (int set = 0; set < nsets; ++set)
   for (int ky = 0; ky < kh; ++ky) {
+    const int kyw = set * kh + ky;                      // row of the stacked weight tap sets
     if (Cin == 8) {
       for (int q = 0; q < kw_pad / 2; ++q) {            // two taps per MMA, second tap through LBO = one pixel
         if (nmma >= MAX_MMA) { set_error("rows_conv: too many MMAs"); return -1; }
         p.mma_a[nmma] = seg_index(ky, 0, 0) * SEG_BYTES + (2 * q) * 16;
         p.mma_lbo[nmma] = 16;
-        const int koff = (ky * kw_pad + 2 * q) * 8;
+        const int koff = (kyw * kw_pad + 2 * q) * 8;
         p.mma_b[nmma] = (koff / 64) * n_pad * 128 + ((koff % 64) / 16) * 32;
         ++nmma;
       }
     } else {
+      const int pl0 = (in_mode == 2 && set == 1) ? P : 0;   // second set reads the lo planes
       for (int kx = 0; kx < kw; ++kx) {                 // one tap per MMA, second channel plane through LBO
         if (nmma >= MAX_MMA) { set_error("rows_conv: too many MMAs"); return -1; }
         int par = 0, shift_px = kx;
         if (stride == 2) { par = (kx == 1) ? 0 : 1; shift_px = (kx == 0) ? 0 : 1; }
-        p.mma_a[nmma] = seg_index(ky, 0, par) * SEG_BYTES + shift_px * 16;
-        p.mma_lbo[nmma] = (seg_index(ky, 1, par) - seg_index(ky, 0, par)) * SEG_BYTES;
-        const int koff = (ky * kw + kx) * 16;
+        p.mma_a[nmma] = seg_index(ky, pl0, par) * SEG_BYTES + shift_px * 16;
+        p.mma_lbo[nmma] = (seg_index(ky, pl0 + 1, par) - seg_index(ky, pl0, par)) * SEG_BYTES;
+        const int koff = (kyw * kw + kx) * 16;
         p.mma_b[nmma] = (koff / 64) * n_pad * 128 + ((koff % 64) / 16) * 32;
         ++nmma;
       }
@@ -303,7 +332,13 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
     if (r != CUDA_SUCCESS) { set_error("rows_conv: cuTensorMapEncodeTiled(w) failed (%d)", static_cast<int>(r)); return -1; }
   }
   const int stage_stride = (nseg * SEG_BYTES + 1023) & ~1023;
-  const int smem = ((p.nkb * n_pad * 128 + 1023) & ~1023) + R_STAGES * stage_stride + 1024 + 1024;
+  const int w_bytes = (p.nkb * n_pad * 128 + 1023) & ~1023;
+  int nst = (113 * 1024 - w_bytes - 3072) / stage_stride;            // two CTAs per SM whenever >= 2 stages fit
+  if (nst < 2) nst = (226 * 1024 - w_bytes - 3072) / stage_stride;
+  if (nst > R_STAGES) nst = R_STAGES;
+  if (nst < 2) { set_error("rows_conv: row segments do not fit in shared memory"); return -1; }
+  p.nstages = nst;
+  const int smem = w_bytes + nst * stage_stride + 1024 + 2048;
   const int tiles = B * p.Ho * ((p.Wo + RBM - 1) / RBM);
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);

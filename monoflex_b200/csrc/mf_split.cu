@@ -102,6 +102,34 @@ int launch_pack_image_split(const float* x, __half* y, int B, int C, int H, int 
   return check_cuda(cudaGetLastError(), "pack_image_split");
 }
 
+// image -> ONE 16-byte-pixel plane [hi3 | lo3 | 0 0] for the row-segment stem kernel (mf_rows.cu, in_mode 1)
+__global__ void pack_image_pair8_kernel(const float* __restrict__ x, __half* __restrict__ y, int B, int C, long long HW) {
+  pdl_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const long long b = i / HW, pix = i - b * HW;
+  __half o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = __float2half_rn(0.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c < C) {
+      const float v = __ldg(x + (b * C + c) * HW + pix);
+      const __half hi = __float2half_rn(v);
+      o[c] = hi;
+      o[3 + c] = __float2half_rn(v - __half2float(hi));
+    }
+  }
+  *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<uint4*>(&o[0]);
+}
+int launch_pack_image_pair8(const float* x, __half* y, int B, int C, int H, int W, cudaStream_t st) {
+  if (C > 3) { set_error("pack_image_pair8: C=%d > 3", C); return -1; }
+  const long long n = static_cast<long long>(B) * H * W;
+  (void)launch_k(pack_image_pair8_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, y, B, C,
+                 static_cast<long long>(H) * W);
+  return check_cuda(cudaGetLastError(), "pack_image_pair8");
+}
+
 // ---------------------------------------------------------------- MaxPool2d(2) on hi/lo rows
 __global__ void maxpool2_split_kernel(const __half* __restrict__ x, int x_lo, __half* __restrict__ y, int y_lo, int B, int H,
                                       int W, int C, int x_ld, int y_ld) {

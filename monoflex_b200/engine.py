@@ -65,7 +65,10 @@ class Act(object):
         the planar stem layout [B][H][C/8 x npar][W/npar][8])."""
         if self.npar:
             P, Wg = self.C // 8, self.W // self.npar
-            v = self.buf.view(self.B, self.H, P, self.npar, Wg, 8).permute(0, 2, 5, 1, 4, 3)
+            if self.split:          # pair planes: hi planes then lo planes
+                v = self.buf.view(self.B, self.H, 2, P, self.npar, Wg, 8).float().sum(2).permute(0, 2, 5, 1, 4, 3)
+            else:
+                v = self.buf.view(self.B, self.H, P, self.npar, Wg, 8).permute(0, 2, 5, 1, 4, 3)
             return v.reshape(self.B, self.C, self.H, self.W)
         if self.split:
             # hi + lo as a fresh fp32 NCHW tensor (one small kernel); `_mf_act` lets the predictor find the pair rows again
@@ -121,11 +124,17 @@ class Plan(object):
     def add(self, fn_name, argbuilder):
         self.ops.append((fn_name, argbuilder))
 
+    def add_py(self, fn):
+        """a host callable executed in launch order by run() (device-side torch ops only: no host sync, graph-capturable).
+        Train-mode plans use it to refresh what an inference plan bakes in at build time - derived copies of parameters
+        that the optimiser changes every step."""
+        self.ops.append(("__py__", fn))
+
     def finalize(self):
         for a in self.acts:
             if a.owner is None and a.buf is None:          # a.buf already set = caller-owned storage bound before finalize
                 if a.npar:
-                    a.buf = torch.empty(a.M * a.C // 8, 8, dtype=torch.half, device=self.device)
+                    a.buf = torch.empty((2 if a.split else 1) * a.M * a.C // 8, 8, dtype=torch.half, device=self.device)
                 else:
                     a.buf = torch.empty(a.M, (2 if a.split else 1) * a.C, dtype=torch.half, device=self.device)
         for a in self.acts:
@@ -138,13 +147,18 @@ class Plan(object):
                 a.owner = None
         lib = _lib.load()
         for fn_name, argbuilder in self.ops:
-            self.launches.append((getattr(lib, fn_name), tuple(argbuilder()), fn_name))
+            if fn_name == "__py__":
+                self.launches.append((argbuilder, None, fn_name))
+            else:
+                self.launches.append((getattr(lib, fn_name), tuple(argbuilder()), fn_name))
         self.n_launch = len(self.launches)
 
     def run(self):
         st = torch.cuda.current_stream().cuda_stream
         for fn, args, name in self.launches:
-            if fn(*args, st) != 0:
+            if args is None:
+                fn()
+            elif fn(*args, st) != 0:
                 raise RuntimeError("%s failed: %s" % (name, _lib.load().mf_last_error().decode()))
 
     def run_timed(self):
@@ -155,7 +169,10 @@ class Plan(object):
         for fn, args, name in self.launches:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(st)
-            if fn(*args, st.cuda_stream) != 0:
+            if args is None:
+                fn()
+                args = ()
+            elif fn(*args, st.cuda_stream) != 0:
                 raise RuntimeError("%s failed: %s" % (name, _lib.load().mf_last_error().decode()))
             b.record(st)
             evs.append((name, args, a, b))
@@ -166,6 +183,25 @@ class Plan(object):
     def pack_weight(self, w, cin_pad=None, split=False):
         """OIHW (or OIW for Conv1d) fp32 parameter -> packed fp16 [n_pad, k_pad] device tensor. split=True: hi/lo pair
         weights in the tripled virtual K order of a split-input GEMM (mf_pack_conv_weight_split)."""
+        if isinstance(w, (list, tuple)):
+            # train mode: several parameters stacked along the output-channel axis (the nine head branches), each re-packed
+            # from its LIVE storage on every run
+            assert self.train and not split and cin_pad is None
+            parts = [t.detach() for t in w]
+            cout = sum(t.shape[0] for t in parts)
+            _, cin, kh, kw = parts[0].shape
+            bn = _lib.load().mf_conv_block_n(cout)
+            assert all(t.shape[0] % bn == 0 and t.dtype == torch.float32 and t.is_contiguous() for t in parts)
+            k_pad = (kh * kw * cin + 63) // 64 * 64
+            out = torch.empty(cout, k_pad, dtype=torch.half, device=self.device)
+            self.keep.append(out)
+            row = 0
+            for t in parts:
+                self.add("mf_pack_conv_weight", lambda t=t, row=row: (t.data_ptr(), t.shape[0], cin, kh, kw, cin, t.shape[0], k_pad,
+                                                                        out.data_ptr() + 2 * row * k_pad))
+                row += t.shape[0]
+            return out, cout, k_pad
+        live = self.train and w.dtype == torch.float32 and w.is_contiguous()
         w = w.detach().float().contiguous()
         if w.dim() == 3:
             w = w.unsqueeze(2)   # Conv1d: [O, I, 1, k]
@@ -182,8 +218,15 @@ class Plan(object):
             return out, n_pad, k_pad
         k_pad = (kh * kw * cin_pad + 63) // 64 * 64
         out = torch.empty(n_pad, k_pad, dtype=torch.half, device=self.device)
-        _lib.call("mf_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr(),
-                  _lib.stream())
+        if live:
+            # train mode: `w` aliases the parameter's storage (the optimiser updates it in place), so the repack is a plan op
+            # executed on every run instead of once at build time - the plan itself stays valid across optimiser steps
+            self.keep.append(w)
+            self.add("mf_pack_conv_weight", lambda: (w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr()))
+        else:
+            assert not self.train or not w.requires_grad
+            _lib.call("mf_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr(),
+                      _lib.stream())
         self.keep.append(out)
         return out, n_pad, k_pad
 
@@ -191,6 +234,14 @@ class Plan(object):
         """Fold eval-mode BatchNorm (dla_dcn.py:76 etc.) / InPlaceABN (|w|+eps) and the conv bias into (scale, shift)."""
         scale = torch.ones(n_pad, dtype=torch.float32, device=self.device)
         shift = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
+        if self.train:
+            # train-mode plans never fold normalisation layers; a conv bias is re-read from the live parameter on every run
+            assert bn is None
+            if conv_bias is not None:
+                b = conv_bias.detach()
+                self.add_py(lambda: shift[:cout].copy_(b))
+            self.keep.extend([scale, shift])
+            return scale, shift
         if bn is not None:
             w = bn.weight.detach().float()
             if abs_weight:
@@ -227,7 +278,10 @@ class Plan(object):
 
     def conv(self, x, weight, stride, pad, bn=None, bias=None, act=ACT_RELU, residual=None, out=None, abs_weight=False,
              cin_pad=None):
-        cout, _, kh, kw = weight.shape if weight.dim() == 4 else (weight.shape[0], weight.shape[1], 1, weight.shape[2])
+        if isinstance(weight, (list, tuple)):       # train mode: parameters stacked along Cout, see pack_weight
+            cout, (_, _, kh, kw) = sum(t.shape[0] for t in weight), weight[0].shape
+        else:
+            cout, _, kh, kw = weight.shape if weight.dim() == 4 else (weight.shape[0], weight.shape[1], 1, weight.shape[2])
         if self.train and bn is not None:
             # training mode: raw convolution (+ bias), then batch-statistics normalisation + residual + activation
             assert not isinstance(pad, tuple), "non-square padding is not built"
@@ -311,10 +365,38 @@ class Plan(object):
             shift.data_ptr(), ACT_RELU, OUT_F16_NHWC, y.ptr(), y.ld))
         return y
 
-    def planar_act(self, B, H, W, C, npar):
-        a = self.act(B, H, W, C)
+    def planar_act(self, B, H, W, C, npar, split=False):
+        a = self.act(B, H, W, C, split=split)
         a.npar = npar
         return a
+
+    def conv_rows_strict(self, x, weight, stride, pad, bn, out_planar, out_npar=1, image=False):
+        """Strict-precision stem convolution on 16-byte-pixel planes (mf_conv2d_rows_f16x2). image=True: x is the image pair
+        plane [hi3 | lo3 | 0 0] (8 channels, mf_pack_image_pair8) and the weights are two stacked tap sets [W_hi | W_hi | 0 0],
+        [W_lo | 0 ...]; else x is a planar pair activation (planes hi0 hi1 lo0 lo1) and the weights three stacked sets W_hi,
+        W_hi, W_lo. The extra products are extra MMAs over the same resident row segments. Output: pair, planar or NHWC rows."""
+        cout, cin_w, kh, kw = weight.shape
+        w = weight.detach().float()
+        w_hi = w.half().float()
+        w_lo = (w - w_hi).half().float()
+        if image:
+            assert x.C == 8 and cin_w == 3 and not x.split
+            wa = torch.zeros(cout, 8, kh, 8, dtype=torch.float32, device=w.device)
+            wb = torch.zeros_like(wa)
+            wa[:, 0:3, :, :kw], wa[:, 3:6, :, :kw], wb[:, 0:3, :, :kw] = w_hi, w_hi, w_lo
+            wv, cin, in_mode, in_npar = torch.cat([wa, wb], 2), 8, 1, 1
+        else:
+            assert x.C == 16 and x.split and x.npar == 1 and stride == 1
+            wv, cin, in_mode, in_npar = torch.cat([w_hi, w_hi, w_lo], 2), 16, 2, 1
+        wp, n_pad, k_pad = self.pack_weight(wv.contiguous(), cin_pad=cin)
+        scale, shift = self.affine(cout, n_pad, bn)
+        Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1
+        y = self.planar_act(x.B, Ho, Wo, cout, out_npar, split=True) if out_planar else self.act(x.B, Ho, Wo, cout, split=True)
+        self.add("mf_conv2d_rows_f16x2", lambda: (
+            x.ptr(), x.B, x.H, x.W, cin, in_npar, in_mode, wp.data_ptr(), n_pad, k_pad, kh, kw, stride, pad, cout,
+            scale.data_ptr(), shift.data_ptr(), ACT_RELU, 1 if out_planar else 0, out_npar, y.ptr(),
+            y.ld if not out_planar else 8, y.lo if not out_planar else 0))
+        return y
 
     def conv_rows(self, x, weight, stride, pad, bn, out_planar, out_npar=1):
         """Stem convolution on 16-byte-pixel planes (csrc/mf_rows.cu): x is the packed image (8 ch) or a planar
@@ -351,6 +433,9 @@ class Plan(object):
         assert k == 2 * f and C == x.C
         wt = up_weight.detach().float().reshape(C, k * k).t().contiguous()   # [k*k, C]
         self.keep.append(wt)
+        if self.train:                         # trainable depth-wise kernel: refresh the tap-major copy on every run
+            uw = up_weight.detach()
+            self.add_py(lambda: wt.copy_(uw.reshape(C, k * k).t()))
         y = self.act(x.B, x.H * f, x.W * f, C)
         if x.split:
             assert y.split and (skip is None or skip.split)
@@ -366,11 +451,19 @@ class Plan(object):
         return y
 
 
-def fingerprint(module):
-    """Cheap change detector for cached plans: parameter/buffer versions + training flag."""
-    v = 0
-    for t in module.parameters():
-        v += t._version
+def fingerprint(module, versions=True):
+    """versions=False: addresses only - the key of train-mode plans, which read every parameter from its live storage on
+    each run and therefore survive optimiser steps.
+    Change detector for cached plans: (storage address, version) of every parameter and buffer + training flag. The
+    address catches a ParamArena re-binding `p.data` (no version bump); versions catch optimiser steps, load_state_dict and
+    the running-statistics updates of the train-mode BatchNorm kernels (`bump_buffers`)."""
+    sig = tuple((t.data_ptr(), t._version if versions else 0) for t in module.parameters()) + \
+        tuple((t.data_ptr(), t._version if versions else 0) for t in module.buffers())
+    return (hash(sig), module.training, next(module.parameters()).device)
+
+
+def bump_buffers(module):
+    """the bn_train kernels update running_mean / running_var behind torch's back: bump their versions so that an eval plan
+    or CUDA graph with folded statistics is rebuilt after training steps"""
     for t in module.buffers():
-        v += t._version
-    return (v, module.training, next(module.parameters()).device)
+        torch.autograd.graph.increment_version(t)

@@ -131,8 +131,16 @@ class DLA(nn.Module):
         rows_ok = (len(self.level0) == 3 and len(self.level1) == 3 and self.channels[0] == 16 and x8.W % 2 == 0 and
                    self.level1[0].stride[0] == 2 and os.environ.get("MF_NO_ROWS_STEM", "0") != "1" and not P.train)
         y = []
-        if P.strict:
-            # strict precision: x8 is the 16-channel pair-packed image [hi3 | lo3 | hi3 | 0 x 7] (mf_pack_image_split), so the
+        if P.strict and rows_ok:
+            # strict precision on the row-segment kernel: x8 is the image pair plane [hi3 | lo3 | 0 0] (mf_pack_image_pair8);
+            # 7x7 and level0 run as extra MMAs over the same resident row segments, level0 hands NHWC pair rows to level1
+            x8.npar = 1
+            a0 = P.conv_rows_strict(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], out_planar=True, image=True)
+            a1 = P.conv_rows_strict(a0, self.level0[0].weight, 1, 1, self.level0[1], out_planar=False)
+            x = P.conv(a1, self.level1[0].weight, self.level1[0].stride[0], 1, self.level1[1])
+            y += [a1, x]
+        elif P.strict:
+            # generic fallback: x8 is the 16-channel pair-packed image [hi3 | lo3 | hi3 | 0 x 7] (mf_pack_image_split), so the
             # 7x7 stem is a plain 16-channel conv whose per-tap weights are [W_hi | W_hi | W_lo | 0]: the three split products
             # A_hi W_hi + A_lo W_hi + A_hi W_lo in one pass. Its output and everything after it are hi/lo pairs.
             w = self.base_layer[0].weight.detach().float()
@@ -254,7 +262,10 @@ class DLASeg(nn.Module):
     def build_plan(self, B, H, W, device):
         strict = (not self.training) and self._precision() == "strict"
         P = engine.Plan(device, train=self.training, strict=strict)
-        x8 = P.act(B, H, W, 16, split=False) if strict else P.act(B, H, W, 8)
+        import os
+        self._strict_rows = strict and os.environ.get("MF_NO_ROWS_STEM", "0") != "1" and W % 2 == 0
+        x8 = P.act(B, H, W, 8 if (self._strict_rows or not strict) else 16, split=False)
+        P.image_pack = "mf_pack_image_pair8" if self._strict_rows else ("mf_pack_image_split" if strict else "mf_pack_image")
         levels = self.base.plan(P, x8)
         ups = self.dla_up.plan(P, levels)
         y = [ups[i] for i in range(self.last_level - self.first_level)]   # the reference's .clone()s are not needed
@@ -268,7 +279,7 @@ class DLASeg(nn.Module):
         return getattr(self, "precision", None) or engine.default_precision()
 
     def _plan_for(self, x):
-        key = (tuple(x.shape), engine.fingerprint(self), self._precision())
+        key = (tuple(x.shape), engine.fingerprint(self, versions=not self.training), self._precision())
         plan = self._plans.get('plan')
         if plan is None or self._plans.get('key') != key:
             B, _, H, W = x.shape
@@ -305,6 +316,6 @@ class DLASeg(nn.Module):
 
     def run_plan(self, plan, x):
         B, C, H, W = x.shape
-        call("mf_pack_image_split" if plan.strict else "mf_pack_image", x.data_ptr(), plan.input.ptr(), B, C, H, W, stream())
+        call(plan.image_pack, x.data_ptr(), plan.input.ptr(), B, C, H, W, stream())
         plan.run()
         self.last_plan = plan

@@ -76,16 +76,17 @@ class KeypointDetector(nn.Module):
         return self._forward_graph(x, targets)
 
     # ------------------------------------------------------------------ training path
-    def _forward_train(self, x, targets):
+    def _forward_train(self, x, targets, prepared=None, sync_log=True):
         """model/detector.py:32-34 + detector_head.py:17-25 in training mode -> (loss_dict, log_loss_dict)."""
         if not x.is_cuda:
             raise RuntimeError("monoflex_b200 trains on sm_100a GPUs only; no CPU fallback")
         features = self.backbone.train_forward(x)
         pred = self.heads.predictor.train_forward(features, targets)
+        engine.bump_buffers(self)               # running statistics were updated by the bn_train kernels
         if self._anchor is None or self._anchor.device != x.device:
             self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
         cls, reg = _TapeBridge.apply(self._anchor, pred['cls'], pred['reg'], self)
-        return self.heads.loss_evaluator({'cls': cls, 'reg': reg}, targets)
+        return self.heads.loss_evaluator({'cls': cls, 'reg': reg}, targets, prepared=prepared, sync_log=sync_log)
 
     def train_forward_losses(self, images, targets):
         """explicit name of the training-mode forward (kept from round 1; same as `model.train(); model(images, targets)`)"""

@@ -110,33 +110,54 @@ class Loss_Computation(object):
         width = load().mf_loss_obj_cols()
         cols.append(torch.zeros(B * self.max_objs, width - used, dtype=torch.float32, device=device))
         obj = torch.cat(cols, 1).contiguous()
+        # per-image calibration (host scalars, cached by value) + pad_size (stacked on the device: no host sync when the
+        # targets already live there)
         rows = []
         for t in targets:
             c = t.get_field("calib")
-            pad = t.get_field("pad_size")
-            rows.append([float(c.f_u), float(c.f_v), float(c.c_u), float(c.c_v), float(c.b_x), float(c.b_y),
-                         float(pad[0]), float(pad[1])])
-        img = torch.tensor(rows, dtype=torch.float32).to(device, non_blocking=True)
+            rows.append((float(c.f_u), float(c.f_v), float(c.c_u), float(c.c_v), float(c.b_x), float(c.b_y)))
+        key = (tuple(rows), str(device))
+        cache = getattr(self, "_calib_cache", None)
+        if cache is None or cache[0] != key:
+            cache = self._calib_cache = (key, torch.tensor(rows, dtype=torch.float32).to(device))
+        pad = torch.stack([torch.as_tensor(t.get_field("pad_size")) for t in targets]).to(device=device, dtype=torch.float32,
+                                                                                         non_blocking=True).view(B, 2)
+        img = torch.cat([cache[1], pad], 1).contiguous()
         return hm, obj, img
 
-    def __call__(self, predictions, targets):
+    def __call__(self, predictions, targets, prepared=None, sync_log=True):
+        """prepared: (hm, obj, img) from `prepare_targets` already on the device (static buffers of a captured training step);
+        sync_log=False: no host read here - log_loss_dict is a `DeferredLog` whose `resolve()` does the step's single D2H copy
+        when the caller wants the numbers (a CUDA-graph capture cannot contain it)."""
         cls, reg = predictions['cls'], predictions['reg']
         if not (cls.is_cuda and reg.is_cuda):
             raise RuntimeError("monoflex_b200 runs on sm_100a GPUs only; no CPU fallback")
         cls, reg = cls.float().contiguous(), reg.float().contiguous()
         if len(targets) != reg.shape[0]:
             raise ValueError("Loss_Computation: %d target lists for a batch of %d" % (len(targets), reg.shape[0]))
-        hm, obj, img = self.prepare_targets(targets, reg.device)
+        hm, obj, img = prepared if prepared is not None else self.prepare_targets(targets, reg.device)
         if hm.shape != cls.shape:
             raise ValueError("Loss_Computation: heat-map label %s vs prediction %s" % (tuple(hm.shape), tuple(cls.shape)))
         out = _FusedLoss.apply(cls, reg, hm, obj, img, self)
         loss_dict = {k: out[i] for i, k in enumerate(REF_LOSS_NAMES)}
-        host = torch.cat([out.detach()[:11], out.detach()[16:16 + len(LOG_KEYS)]]).cpu()  # the step's single D2H read
+        log = DeferredLog(out.detach())
+        return loss_dict, (log.resolve() if sync_log else log)
+
+
+class DeferredLog(object):
+    """the logged scalars of one loss evaluation, still on the device; resolve() -> the reference's log_loss_dict"""
+
+    def __init__(self, out):
+        self.out = out
+
+    def resolve(self):
+        out = self.out
+        host = torch.cat([out[:11], out[16:16 + len(LOG_KEYS)]]).cpu()                    # the step's single D2H read
         log_loss_dict = {k: float(host[11 + i]) for i, k in enumerate(LOG_KEYS)}
         for i, k in enumerate(REF_LOSS_NAMES):                                            # detector_loss.py:478-480
             if k not in log_loss_dict:
                 log_loss_dict[k] = float(host[i])
-        return loss_dict, log_loss_dict
+        return log_loss_dict
 
 
 REF_LOSS_NAMES = ['hm_loss', 'bbox_loss', 'depth_loss', 'offset_loss', 'orien_loss', 'dims_loss', 'corner_loss',

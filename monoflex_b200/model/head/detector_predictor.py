@@ -162,7 +162,9 @@ class _predictor(nn.Module):
         else:
             # train mode: every branch normalises with its own InPlaceABN module (batch statistics, running-stat update)
             norm = [(b[1], i * hc, hc) for i, b in enumerate(branches)] if P.train else abn
-            hid = P.conv(x, w_all, 1, 1, norm, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
+            # train mode: the nine branch weights are re-packed from their live parameters on every run (static plan)
+            w_head = [b[0].weight for b in branches] if P.train else w_all
+            hid = P.conv(x, w_head, 1, 1, norm, act=engine.ACT_LEAKY, abs_weight=True)   # [B,H,W,2304]
 
             def slice_of(i):
                 sl = P.act(B, H, W, hc)
@@ -219,7 +221,7 @@ class _predictor(nn.Module):
     def plan_for(self, features, K_edge):
         feat = _as_rows(features)
         key = (feat.buf.data_ptr(), feat.ch_off, feat.B, feat.H, feat.W, feat.buf.shape[1], K_edge,
-               engine.fingerprint(self), bool(getattr(feat, "split", False)))
+               engine.fingerprint(self, versions=not self.training), bool(getattr(feat, "split", False)))
         plan = self._plans.get('plan')
         if plan is None or self._plans.get('key') != key:
             plan = self.build_plan(feat, K_edge)
@@ -245,7 +247,8 @@ class _predictor(nn.Module):
 
     def _run(self, features, targets):
         plan = self.plan_for(features, targets[0].get_field("edge_indices").shape[0])
-        self.load_targets(plan, targets)
+        if not getattr(self, "_targets_preloaded", False):     # a captured training step loads them before the replay
+            self.load_targets(plan, targets)
         plan.run()
         return {'cls': plan.cls, 'reg': plan.reg}
 

@@ -112,11 +112,19 @@ class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW(model_params, lr, betas=(0.9, 0.99), weight_decay) (solver/__init__.py:36-37) with the update of
     ALL tensors in one kernel launch over a ParamArena."""
 
-    def __init__(self, params, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-5, symmetric_group=None):
-        """symmetric_group: a torch.distributed process group (NCCL, one rank per GPU of ONE NVLink domain). When given,
+    def __init__(self, params, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-5, symmetric_group=None,
+                 capturable=True, check_finite=True):
+        """capturable (default): `step()` keeps the step count on the device and guards the update with a finite scan of the
+        gradient arena (`mf_adamw_step_dyn`: a non-finite gradient skips the update, `skipped_steps()` counts them), so a
+        whole training step can be captured in one CUDA graph; capturable=False is the host-scalar `mf_adamw_step` launch.
+        symmetric_group: a torch.distributed process group (NCCL, one rank per GPU of ONE NVLink domain). When given,
         the parameter and gradient arenas are allocated in symmetric (peer-mapped) memory and `step_exchange()` replaces
         `allreduce_grads(); step(grad_scale=1/world)` by the fused reduce-scatter + AdamW + all-gather kernel."""
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # amsgrad / maximize / foreach / capturable / differentiable / fused: the keys torch.optim.AdamW.load_state_dict
+        # expects in every param group, so a checkpoint written here loads into the reference's optimiser and vice versa
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                                      foreach=None, capturable=False, differentiable=False, fused=None))
+        self.capturable, self.check_finite = bool(capturable), bool(check_finite)
         tensors = [p for g in self.param_groups for p in g["params"]]
         if len({id(p) for p in tensors}) != len(tensors):
             raise ValueError("FusedAdamW: a parameter appears in more than one group")
@@ -145,6 +153,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self._lr_key = None
         self._chunk_lr = None
+        self._skip = [False] * len(self.arena.tensors)     # tensors outside the forward graph (autograd leaves their grad None)
+        dev = self.arena.params.device
+        self._state4 = torch.zeros(4, dtype=torch.int64, device=dev)      # [step, found-non-finite, skipped steps, -]
+        self._dyn16 = torch.zeros(4, dtype=torch.float32, device=dev)
         self._bind_state()
 
     # -- torch.optim plumbing ---------------------------------------------------------------------------------------
@@ -169,6 +181,8 @@ class FusedAdamW(torch.optim.Optimizer):
         if len(steps) > 1:
             raise ValueError("FusedAdamW: per-tensor step counts differ in the checkpoint: %s" % sorted(steps))
         self.step_count = steps.pop() if steps else 0
+        self._state4.zero_()
+        self._state4[0] = self.step_count
         self._bind_state()
         self._lr_key = None
 
@@ -177,11 +191,30 @@ class FusedAdamW(torch.optim.Optimizer):
         self.arena.grads.zero_()
 
     def _lr_table(self):
-        lrs = tuple(g["lr"] for g in self.param_groups for _ in g["params"])
+        lrs = tuple(0.0 if skip else g["lr"] for (g, skip) in zip((g for g in self.param_groups for _ in g["params"]), self._skip))
         if lrs != self._lr_key:
-            self._chunk_lr = self.arena.chunk_table(lrs).to(self.arena.params.device)
+            table = self.arena.chunk_table(lrs).to(self.arena.params.device)
+            if self._chunk_lr is None or self._chunk_lr.shape != table.shape:
+                self._chunk_lr = table
+            else:
+                self._chunk_lr.copy_(table)               # in place: a captured graph keeps reading the same buffer
             self._lr_key = lrs
         return self._chunk_lr
+
+    def mark_unused(self, names, model):
+        """Parameters the forward never uses (e.g. the outer `project` of DLA's two-level trees, dla_dcn.py:249) get grad None
+        from autograd in the reference and torch's AdamW skips them entirely (no weight decay, no moment update). Their
+        arena gradient is always zero here; this marks them so the kernel skips their chunks too - independently of the
+        param-group lr the scheduler keeps rewriting."""
+        by_id = {id(p): i for i, p in enumerate(self.arena.tensors)}
+        for n, p in model.named_parameters():
+            if n in names and id(p) in by_id:
+                self._skip[by_id[id(p)]] = True
+        self._lr_key = None
+
+    def skipped_steps(self):
+        """number of optimiser steps skipped because the gradient arena held a non-finite value (host sync)"""
+        return int(self._state4[2].item())
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
@@ -202,6 +235,17 @@ class FusedAdamW(torch.optim.Optimizer):
         table = self._lr_table()
         self.step_count += 1
         b1, b2 = self.defaults["betas"]
+        if self.capturable:
+            if self.step_count == 1 and int(self._state4[0].item()) != 0:
+                raise RuntimeError("FusedAdamW: device step counter out of sync")
+            _lib.call("mf_adamw_step_dyn", self.arena.params.data_ptr(), self.arena.grads.data_ptr(), self.exp_avg.data_ptr(),
+                      self.exp_avg_sq.data_ptr(), table.data_ptr(), self.arena.n_chunks, b1, b2, self.defaults["eps"],
+                      self.defaults["weight_decay"], float(grad_scale), 1.0, self._state4.data_ptr(), self._dyn16.data_ptr(),
+                      1 if self.check_finite else 0, torch.cuda.current_stream().cuda_stream)
+            self._step_t += 1
+            for p in self.arena.tensors:
+                torch.autograd.graph.increment_version(p)
+            return None
         _lib.call("mf_adamw_step", self.arena.params.data_ptr(), self.arena.grads.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), table.data_ptr(), self.arena.n_chunks, b1, b2, self.defaults["eps"],
                   self.defaults["weight_decay"], self.step_count, float(grad_scale), 1.0,
@@ -255,8 +299,10 @@ def build_optimizer(model, cfg):
                       betas=(0.9, 0.99))
 
 
-def build_scheduler(optimizer, optim_cfg, last_epoch=-1):
-    """solver/__init__.py:64-92 without the fastai one-cycle branch: multi-step LambdaLR (+ no warm-up, LR_WARMUP False)."""
+def build_scheduler(optimizer, optim_cfg, last_epoch=-1, total_iters_each_epoch=None):
+    """solver/__init__.py:64-92 without the fastai one-cycle branch: multi-step LambdaLR (+ no warm-up, LR_WARMUP False).
+    Same keyword interface as the reference (`build_scheduler(optimizer, total_iters_each_epoch=..., optim_cfg=...)`,
+    tools/plain_train_net.py:86-90); `total_iters_each_epoch` only feeds the one-cycle branch and is ignored."""
     decay_steps = optim_cfg.STEPS
 
     def lr_lbmd(cur_epoch):

@@ -154,6 +154,38 @@ def test_strict_stem_and_elementwise():
     assert rel_err(gu, ru) < STRICT_TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 10, 144), (1, 7, 256), (1, 5, 40)])
+def test_strict_stem_rows_chain(shape):
+    """strict stem on the row-segment kernel (mf_conv2d_rows_f16x2): image pair plane -> 7x7 (two tap sets over the same
+    resident rows) -> planar pair planes -> 3x3 (three tap sets) -> NHWC pair rows -> 3x3 stride 2 (gather GEMM on pairs)."""
+    from monoflex_b200._lib import call, stream
+    B, H, W = shape
+    gen = np.random.Generator(np.random.PCG64(17))
+    x = torch.from_numpy(gen.standard_normal((B, 3, H, W)).astype(np.float32))
+    w0 = torch.from_numpy((gen.standard_normal((16, 3, 7, 7)) / 12).astype(np.float32))
+    w1 = torch.from_numpy((gen.standard_normal((16, 16, 3, 3)) / 12).astype(np.float32))
+    w2 = torch.from_numpy((gen.standard_normal((32, 16, 3, 3)) / 12).astype(np.float32))
+    bn0, bn1, bn2 = FakeBN(16, gen), FakeBN(16, gen), FakeBN(32, gen)
+    P = engine.Plan("cuda", strict=True)
+    x8 = P.act(B, H, W, 8, split=False)
+    x8.npar = 1
+    a0 = P.conv_rows_strict(x8, w0.cuda(), 1, 3, bn0, out_planar=True, image=True)
+    a1 = P.conv_rows_strict(a0, w1.cuda(), 1, 1, bn1, out_planar=False)
+    a2 = P.conv(a1, w2.cuda(), 2, 1, bn2)
+    P.finalize()
+    xc = x.cuda()
+    call("mf_pack_image_pair8", xc.data_ptr(), x8.ptr(), B, 3, H, W, stream())
+    P.run()
+    torch.cuda.synchronize()
+    g0, g1, g2 = (t.nchw_view().float().cpu() for t in (a0, a1, a2))
+    r0 = F.relu(bn0.cpu_apply(F.conv2d(x.double(), w0.double(), None, 1, 3).float()))
+    assert rel_err(g0, r0) < STRICT_TOL
+    r1 = F.relu(bn1.cpu_apply(F.conv2d(g0.double(), w1.double(), None, 1, 1).float()))
+    assert rel_err(g1, r1) < STRICT_TOL
+    r2 = F.relu(bn2.cpu_apply(F.conv2d(g1.double(), w2.double(), None, 2, 1).float()))
+    assert rel_err(g2, r2) < STRICT_TOL
+
+
 @pytest.mark.parametrize("case", DCN_CASES_EARLY)
 def test_dcn_strict_pairs(case):
     """fused DCNv2 on pairs vs the fp32 oracle restatement of the reference's im2col + GEMM (pinned bit-for-bit to the

@@ -175,3 +175,23 @@ def test_train_step_oracle_matches_reference_train_mode():
     for k in ("backbone.base.base_layer.0.weight", "backbone.base.level2.tree1.bn1.weight", "heads.predictor.class_head.2.bias"):
         ref = gold["grad_" + k]
         assert np.abs(sd[k].grad.numpy() - ref).max() <= 2e-3 * np.abs(ref).max(), k
+
+
+def test_input_pipeline_oracle_vs_reference_golden():
+    """N4: pad_image + ToTensor + Normalize and the heat-map drawing restated in oracle/input_oracle.py reproduce the unmodified
+    reference functions (oracle/make_golden_input.py) bit for bit."""
+    from oracle import input_oracle as io
+    from monoflex_b200.data import gaussian_radius
+    with np.load(os.path.join(GOLDEN, "input_pipeline.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    imgs, obj = io.synthetic_case(seed=0)
+    assert np.array_equal(obj, g["obj"])
+    for b, im in enumerate(imgs):
+        padded, pad = io.pad_image(im, 384, 1280)
+        t = io.to_tensor_normalize(padded, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]).numpy()
+        assert np.array_equal(pad, g["pads"][b])
+        assert np.array_equal(t[:, ::7, ::11], g["image_samples"][b])
+        assert t.astype(np.float64).sum() == g["image_sums"][b]
+    assert np.array_equal(io.draw_heatmaps(obj, 3, 96, 320), g["hm"])
+    got = np.array([gaussian_radius(h, w) for h, w in ((10.0, 20.0), (3.5, 7.25), (40.0, 12.0), (1.0, 1.0), (96.0, 300.0))])
+    assert np.array_equal(got, g["radii"])
