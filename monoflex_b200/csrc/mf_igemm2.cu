@@ -385,51 +385,24 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       const uint32_t prm_o = prm_w + 9 * BM * 16;                    // [9*128] int4 corner pixel indices
       int stage = 0;
       uint32_t phase = 0;
-      // The (dy, dx, mask) triple of every (pixel, tap) of the NEXT tile is fetched into registers while the current tile's
-      // gather runs: phase P then is arithmetic only (ncu, round 2: the exposed latency of these loads was ~25 % of the
-      // kernel's stall samples - all 16 producer warps waited on them together while the MMA warp starved).
-      constexpr int NI = (9 * BM + NPT - 1) / NPT;
-      float pf[NI][3];
-      auto prefetch_om = [&](const int t) {
-        const int m_tile = t / ntn;
-        const int tile_b = m_tile / (tiles_x * tiles_y);
-        const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
-        const int tile_y0 = (tile_t / tiles_x) << 3, tile_x0 = (tile_t % tiles_x) << 4;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int item = tid + i * NPT;
-          const int tap = item >> 7, r = item & (BM - 1);
-          const int yy = tile_y0 + (r >> 4), xx = tile_x0 + (r & 15);
-          pf[i][0] = pf[i][1] = pf[i][2] = 0.f;
-          if (item < 9 * BM && yy < p.H && xx < p.W) {
-            const float* om = p.offmask + (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
-            pf[i][0] = __ldg(om + 2 * tap);
-            pf[i][1] = __ldg(om + 2 * tap + 1);
-            pf[i][2] = __ldg(om + 18 + tap);
-          }
-        }
-      };
-      if (static_cast<int>(blockIdx.x) < ntiles) prefetch_om(blockIdx.x);
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m_tile = t / ntn;
         const int tile_b = m_tile / (tiles_x * tiles_y);
         const int tile_t = m_tile - tile_b * (tiles_x * tiles_y);
         const int tile_y0 = (tile_t / tiles_x) << 3, tile_x0 = (tile_t % tiles_x) << 4;
         bar_sync_named(2, NPT);                              // previous tile's gather no longer reads the records
-#pragma unroll
-        for (int pi = 0; pi < NI; ++pi) {
-          const int item = tid + pi * NPT;
-          if (item >= 9 * BM) break;
+        for (int item = tid; item < 9 * BM; item += NPT) {
           const int tap = item >> 7, r = item & (BM - 1);
           const int yy = tile_y0 + (r >> 4), xx = tile_x0 + (r & 15);
           float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
           int4 o = make_int4(0, 0, 0, 0);
           if (yy < p.H && xx < p.W) {
+            const float* om = p.offmask + (static_cast<long long>(tile_b * p.H + yy) * p.W + xx) * p.om_ld;
             const int ky = tap / 3, kx = tap - ky * 3;
-            const float h_im = static_cast<float>(yy - 1 + ky) + pf[pi][0];
-            const float w_im = static_cast<float>(xx - 1 + kx) + pf[pi][1];
+            const float h_im = static_cast<float>(yy - 1 + ky) + __ldg(om + 2 * tap);
+            const float w_im = static_cast<float>(xx - 1 + kx) + __ldg(om + 2 * tap + 1);
             if (h_im > -1.f && w_im > -1.f && h_im < static_cast<float>(p.H) && w_im < static_cast<float>(p.W)) {
-              const float mk = pf[pi][2];
+              const float mk = __ldg(om + 18 + tap);
               const float hlf = floorf(h_im), wlf = floorf(w_im);
               const float lh = h_im - hlf, lw = w_im - wlf, hh = 1.f - lh, hw = 1.f - lw;
               const int hl = static_cast<int>(hlf), wl = static_cast<int>(wlf), hi = hl + 1, wi = wl + 1;
@@ -447,7 +420,6 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           sts128(prm_o + item * 16, make_uint4(o.x, o.y, o.z, o.w));
         }
         bar_sync_named(2, NPT);
-        if (t + static_cast<int>(gridDim.x) < ntiles) prefetch_om(t + gridDim.x);   // in flight during this tile's gather
         const char* x_img = reinterpret_cast<const char*>(p.x + static_cast<long long>(tile_b) * p.H * p.W * p.x_ld + j * 8);
         int tap = 0, c0 = 0;
         uint32_t dst_off[PASSES];

@@ -16,7 +16,14 @@ from oracle.make_golden_loss import ref_train_targets   # noqa: E402
 from monoflex_b200 import synthetic as syn    # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
-FULL = ["backbone.base.base_layer.0.weight", "backbone.base.level2.tree1.bn1.weight", "heads.predictor.class_head.2.bias"]
+FULL = ["backbone.base.base_layer.0.weight", "backbone.base.level2.tree1.bn1.weight", "heads.predictor.class_head.2.bias",
+        # round 2: element-wise gradient checks along the whole depth of the network (small tensors, stored in full)
+        "backbone.base.level0.0.weight", "backbone.base.level1.0.weight", "backbone.base.level1.1.weight",
+        "backbone.base.level2.tree1.conv1.weight", "backbone.base.level3.tree1.tree1.bn1.bias",
+        "backbone.base.level5.root.bn.weight", "backbone.dla_up.ida_2.up_3.weight",
+        "backbone.ida_up.node_1.conv.weight", "backbone.ida_up.node_1.conv.bias",
+        "backbone.ida_up.node_1.conv.conv_offset_mask.bias", "backbone.ida_up.node_1.actf.0.weight",
+        "heads.predictor.class_head.1.weight", "heads.predictor.reg_heads.2.0.weight", "heads.predictor.trunc_heatmap_conv.1.bias"]
 
 
 def main(batch=2):

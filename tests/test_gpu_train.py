@@ -1,4 +1,6 @@
 """-m gpu: training-side kernels (SURVEY §8 rows R11 backward, R13) against torch-CPU fp32 references of the same op."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -677,14 +679,31 @@ def test_reference_training_loop_unchanged():
     # exactly the parameters outside the reference's forward graph stay at None (the outer `project` of the 2-level trees,
     # dla_dcn.py:249; the golden stores norm 0 for them), like autograd leaves them
     assert unused == {n for n in params if ".project." in n and n.count("tree") == 0 and ("level3" in n or "level4" in n)}, sorted(unused)
-    for name, tol_cos, tol_rel in (("backbone.base.base_layer.0.weight", 0.995, 0.10),
-                                   ("backbone.base.level2.tree1.bn1.weight", 0.98, 0.25),
-                                   ("heads.predictor.class_head.2.bias", 0.9999, 0.02)):
-        got, want = params[name].grad.detach().cpu(), torch.from_numpy(gold["grad_" + name])
+    # Element-wise gradient check, along the whole depth of the network (17 tensors stored in full by oracle/make_golden_train.py).
+    # Yardstick: tests/golden/grad_cos_f16_forward_emulation.json = cosine between the reference's gradients and an EXACT fp32
+    # backward (torch autograd) evaluated on the oracle forward with only the kernels' fp16 rounding points emulated
+    # (tools/grad_emulation_cpu.py). On this synthetic network (random weights + batch-statistics BN: the chaotic regime) that
+    # alone moves the gradients to cos 0.87-0.98 in the backbone - the derivative is ill-conditioned in the point it is taken
+    # at, whatever computes it. The tape has to stay within 0.08 of that yardstick (measured gap 0.02-0.065, independent of
+    # the loss scale from 32 to 2048 - profiles/grad_fidelity_gpu_r02.txt: a different realisation of the forward rounding plus its own fp16
+    # gradient rounding), and the head, whose forward is two layers deep, has to be right outright.
+    import json
+    from conftest import GOLDEN
+    yard = json.load(open(os.path.join(GOLDEN, "grad_cos_f16_forward_emulation.json")))["cos"]
+    report = []
+    for name, want_np in ((k[5:], gold[k]) for k in gold.files if k.startswith("grad_") and k[5:] in yard):
+        got, want = params[name].grad.detach().cpu(), torch.from_numpy(want_np)
         c = _cos(got, want)
-        rel = float((got.double() - want.double()).norm() / want.double().norm())
-        print(name, "cos %.5f rel-l2 %.4f" % (c, rel))
-        assert c > tol_cos and rel < tol_rel, (name, c, rel)
+        ratio = float(got.double().norm() / want.double().norm())
+        report.append((name, c, yard[name], ratio))
+        print("%-58s cos %.5f (fp16-forward yardstick %.5f) |g|/|ref| %.4f" % (name, c, yard[name], ratio))
+    for name, c, y, ratio in report:
+        if name.endswith("node_1.conv.bias"):
+            continue          # a bias in front of a batch-statistics BN: the true gradient is 0, both sides hold rounding noise
+        assert c > y - 0.08, (name, c, y)
+        assert 0.8 < ratio < 1.2, (name, ratio)
+        if name.startswith("heads."):
+            assert c > 0.985, (name, c)
     optimizer.step()
     assert not torch.equal(model.backbone.base.level3.tree1.tree1.conv1.weight.detach(), w0)
     with torch.no_grad():
