@@ -322,6 +322,9 @@ def bench_train(args, rank, world, local_rank, config):
     model = KeypointDetector(cfg)
     model.load_state_dict(syn.make_state_dict(0))
     model = model.to(dev)
+    sync_bn = bool(args.sync_bn) and world > 1
+    if sync_bn:                                   # the reference's own conversion call (tools/plain_train_net.py:131-132)
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     use_graph = args.graph != 0
     tr = Trainer(model, cfg, use_cuda_graph=use_graph, graph_warmup=2)
     n_in = 3
@@ -424,10 +427,19 @@ def bench_train(args, rank, world, local_rank, config):
                                       {"what": "bucketed NCCL all-reduce of the 83.8 MB fp32 gradient arena (3 x 32 MB), 1/world "
                                                "folded into the AdamW kernel; after backward, not overlapped",
                                        "ms_per_step_alone": ms_ar, "share_of_step": ms_ar / (ms / args.steps)}),
-                "batchnorm": "per-GPU batch statistics (USE_SYNC_BN False); see DESIGN.md §8"}
+                "batchnorm": ("SyncBatchNorm: statistics over the global batch (reference runs/monoflex.yaml USE_SYNC_BN True), 2C doubles "
+                              "all-reduced per layer and direction" if sync_bn else
+                              "per-GPU batch statistics (USE_SYNC_BN False)")}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL collectives were captured inside the step's CUDA graph (SyncBatchNorm): tearing the communicator down while the
+        # graph still references it hung destroy_process_group on the 2-GPU run of round 2 - drop the graph, drain, then leave
+        # without the teardown (a benchmark process; the driver only needs the JSON line and exit code 0)
+        sys.stdout.flush()
+        tr._graph = None
+        torch.cuda.synchronize()
+        parallel.barrier()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------ inference bench
@@ -500,6 +512,7 @@ def main():
                          "fast: one fp16 pass. Both are measured and reported under `modes`")
     ap.add_argument("--train", action="store_true", help="BASELINE configs[2] / configs[4]: full train step instead of inference")
     ap.add_argument("--graph", type=int, default=1, help="--train: capture the whole step in a CUDA graph (1) or run it eagerly (0)")
+    ap.add_argument("--sync-bn", type=int, default=1, help="--train, N > 1: SyncBatchNorm like the reference's yaml (1, default) or per-GPU statistics (0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch timing table (json) to this path")
     args = ap.parse_args()

@@ -227,6 +227,23 @@ int mf_bn_train_backward(const void* x, int x_ld, const void* dy, int dy_ld, con
                          const float* mean, const float* rstd, const float* scale, int act, void* dx, int dx_ld, void* dres,
                          int dres_ld, float* dgamma, float* dbeta, float* workspace, void* stream);
 
+/* SyncBatchNorm (torch.nn.SyncBatchNorm after the reference's `convert_sync_batchnorm`, tools/plain_train_net.py:131-132): the
+ * train-mode BatchNorm kernels split around the exchange. `sums` is a DEVICE double [2][C] buffer: *_stats writes the local
+ * per-channel sums (forward: sum x, sum x^2; backward: sum g, sum g*xhat, plus the LOCAL dgamma / dbeta that DDP averages like any
+ * gradient), the host all-reduces it (SUM, NCCL, same stream), *_apply normalises with `count` = the global number of elements per
+ * channel. workspace: mf_bn_train_workspace(M, C) bytes. With one rank the pair equals mf_bn_train_forward / _backward. */
+int mf_bn_sync_forward_stats(const void* x, int x_ld, long long M, int C, float* workspace, double* sums, void* stream);
+int mf_bn_sync_forward_apply(const void* x, int x_ld, long long M, int C, const double* sums, double count, const float* gamma,
+                             const float* beta, float eps, float momentum, int abs_gamma, float* running_mean, float* running_var,
+                             const void* res, int res_ld, int act, void* y, int y_ld, float* mean, float* rstd, float* scale,
+                             float* shift, void* stream);
+int mf_bn_sync_backward_stats(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                              const float* mean, const float* rstd, int act, float* workspace, double* sums, float* dgamma,
+                              float* dbeta, void* stream);
+int mf_bn_sync_backward_apply(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                              const float* mean, const float* rstd, const float* scale, const double* sums, double count, int act,
+                              void* dx, int dx_ld, void* dres, int dres_ld, float* workspace, void* stream);
+
 /* diagnostics: D[128,128] = A^T B with A [64,128] and B [64,128] fp16 row-major (reduction index = rows), computed with
  * MN-major tcgen05 operand descriptors - the operand form the weight-gradient GEMM of the training path needs */
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream);

@@ -62,6 +62,10 @@ SIGNATURES = {
     "mf_bn_train_workspace": [_LL, _I],
     "mf_bn_train_forward": [_P, _I, _LL, _I, _P, _P, _F, _F, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "mf_bn_train_backward": [_P, _I, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P],
+    "mf_bn_sync_forward_stats": [_P, _I, _LL, _I, _P, _P, _P],
+    "mf_bn_sync_forward_apply": [_P, _I, _LL, _I, _P, ctypes.c_double, _P, _P, _F, _F, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "mf_bn_sync_backward_stats": [_P, _I, _P, _I, _P, _I, _LL, _I, _P, _P, _I, _P, _P, _P, _P, _P],
+    "mf_bn_sync_backward_apply": [_P, _I, _P, _I, _P, _I, _LL, _I, _P, _P, _P, _P, ctypes.c_double, _I, _P, _I, _P, _I, _P, _P],
     "mf_selftest_mn_major": [_P, _P, _P, _P],
     "mf_loss_obj_cols": [],
     "mf_loss_forward": [_P] * 7 + [_I] * 6 + [_P, _P, _P],

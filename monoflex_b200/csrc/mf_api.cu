@@ -335,6 +335,32 @@ int mf_bn_train_backward(const void* x, int x_ld, const void* dy, int dy_ld, con
                                   static_cast<const __half*>(y), y_ld, M, C, mean, rstd, scale, act, static_cast<__half*>(dx),
                                   dx_ld, static_cast<__half*>(dres), dres_ld, dgamma, dbeta, workspace, MF_STREAM(stream));
 }
+int mf_bn_sync_forward_stats(const void* x, int x_ld, long long M, int C, float* workspace, double* sums, void* stream) {
+  return launch_bn_sync_forward_stats(static_cast<const __half*>(x), x_ld, M, C, workspace, sums, MF_STREAM(stream));
+}
+int mf_bn_sync_forward_apply(const void* x, int x_ld, long long M, int C, const double* sums, double count, const float* gamma,
+                             const float* beta, float eps, float momentum, int abs_gamma, float* running_mean, float* running_var,
+                             const void* res, int res_ld, int act, void* y, int y_ld, float* mean, float* rstd, float* scale,
+                             float* shift, void* stream) {
+  return launch_bn_sync_forward_apply(static_cast<const __half*>(x), x_ld, M, C, sums, count, gamma, beta, eps, momentum, abs_gamma,
+                                      running_mean, running_var, static_cast<const __half*>(res), res_ld, act,
+                                      static_cast<__half*>(y), y_ld, mean, rstd, scale, shift, MF_STREAM(stream));
+}
+int mf_bn_sync_backward_stats(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                              const float* mean, const float* rstd, int act, float* workspace, double* sums, float* dgamma,
+                              float* dbeta, void* stream) {
+  return launch_bn_sync_backward_stats(static_cast<const __half*>(x), x_ld, static_cast<const __half*>(dy), dy_ld,
+                                       static_cast<const __half*>(y), y_ld, M, C, mean, rstd, act, workspace, sums, dgamma, dbeta,
+                                       MF_STREAM(stream));
+}
+int mf_bn_sync_backward_apply(const void* x, int x_ld, const void* dy, int dy_ld, const void* y, int y_ld, long long M, int C,
+                              const float* mean, const float* rstd, const float* scale, const double* sums, double count, int act,
+                              void* dx, int dx_ld, void* dres, int dres_ld, float* workspace, void* stream) {
+  return launch_bn_sync_backward_apply(static_cast<const __half*>(x), x_ld, static_cast<const __half*>(dy), dy_ld,
+                                       static_cast<const __half*>(y), y_ld, M, C, mean, rstd, scale, sums, count, act,
+                                       static_cast<__half*>(dx), dx_ld, static_cast<__half*>(dres), dres_ld, workspace,
+                                       MF_STREAM(stream));
+}
 int mf_selftest_mn_major(const void* a_km, const void* b_kn, float* d_mn, void* stream) {
   return launch_mn_major_selftest(static_cast<const __half*>(a_km), static_cast<const __half*>(b_kn), d_mn, MF_STREAM(stream));
 }

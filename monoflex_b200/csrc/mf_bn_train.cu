@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ scale, const float* __restrict__ sum_g,
                                                            const float* __restrict__ sum_gx, int act, __half* __restrict__ dx,
-                                                           int dx_ld, __half* __restrict__ dres, int dres_ld, long long M, int C) {
+                                                           int dx_ld, __half* __restrict__ dres, int dres_ld, long long M, int C,
+                                                           double count) {
   pdl_wait();
   const int CV = C / 8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
   bn_unpack8(xq, xv);
   bn_unpack8(gq, gv);
   bn_unpack8(yq, yv);
-  const float inv_m = 1.f / static_cast<float>(M);
+  const float inv_m = static_cast<float>(1.0 / count);          // global element count (== M unless SyncBatchNorm)
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float g = gv[e] * bn_act_grad(yv[e], act);
@@ -217,6 +218,51 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
   }
   *reinterpret_cast<uint4*>(dx + row * dx_ld + cv * 8) = bn_pack8(o);
   if (dres != nullptr) *reinterpret_cast<uint4*>(dres + row * dres_ld + cv * 8) = bn_pack8(gr);
+}
+
+// ------------------------------------------------------------------------------------------------ SyncBatchNorm halves
+// torch.nn.SyncBatchNorm (the reference converts every BatchNorm when MODEL.USE_SYNC_BN is set, tools/plain_train_net.py:131-132)
+// normalises with statistics over the batches of ALL ranks. The kernels above are split around the exchange:
+//   forward : bn_partial -> bn_reduce (per-channel local sums, double) | all-reduce of [2][C] doubles | bn_finalize_sums -> bn_apply
+//   backward: bn_partial<BWD> -> bn_reduce (+ local dgamma / dbeta, which DDP averages like every other gradient) |
+//             all-reduce of [2][C] doubles | bn_bwd_apply with the global sums and the global element count
+// The collective itself is issued by the host between the two C-ABI calls (torch.distributed / NCCL on the same stream).
+__global__ void bn_reduce_kernel(const float* __restrict__ part, int ncta, int C, double* __restrict__ sums) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const double s0 = bn_warp_sum(part, ncta, C, 0, c, lane), s1 = bn_warp_sum(part, ncta, C, 1, c, lane);
+  if (lane == 0) { sums[c] = s0; sums[C + c] = s1; }
+}
+__global__ void bn_finalize_sums_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, float momentum, int abs_gamma,
+                                        float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
+                                        float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  float g = gamma[c];
+  if (abs_gamma) g = fabsf(g) + eps;
+  mean_out[c] = static_cast<float>(mean);
+  rstd_out[c] = rstd;
+  scale[c] = g * rstd;
+  shift[c] = beta[c] - static_cast<float>(mean) * g * rstd;
+  if (running_mean != nullptr) {
+    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unb);
+  }
+}
+__global__ void bn_bwd_sums_kernel(const double* __restrict__ sums, int C, float* __restrict__ sum_g, float* __restrict__ sum_gx,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = static_cast<float>(sums[c]), sx = static_cast<float>(sums[C + c]);
+  if (sum_g != nullptr) { sum_g[c] = s; sum_gx[c] = sx; }
+  if (dgamma != nullptr) { dbeta[c] = s; dgamma[c] = sx; }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -281,8 +327,67 @@ int launch_bn_train_backward(const __half* x, int x_ld, const __half* dy, int dy
   const long long n = M * (C / 8);
   (void)launch_k(bn_bwd_apply_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, x_ld, dy, dy_ld, y, y_ld,
                  mean, rstd, scale, static_cast<const float*>(sums), static_cast<const float*>(sums + C), act, dx, dx_ld, dres,
-                 dres_ld, M, C);
+                 dres_ld, M, C, static_cast<double>(M));
   return check_cuda(cudaGetLastError(), "bn_train_backward");
+}
+
+// ---- SyncBatchNorm halves (see above). sums: double [2][C] device buffer the host all-reduces between the two calls.
+int launch_bn_sync_forward_stats(const __half* x, int x_ld, long long M, int C, float* workspace, double* sums, cudaStream_t st) {
+  if (C % 8 || x_ld % 8 || C > 2048 || M < 1) { set_error("bn_sync_forward_stats: bad shape (C=%d)", C); return -1; }
+  long long rpc; int th; size_t sm;
+  const int ncta = bn_grid(M, C, rpc, th, sm);
+  if (ncta < 0 || sm > 64 * 1024) { set_error("bn_sync_forward_stats: C=%d too wide", C); return -1; }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(bn_partial_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(bn_partial_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  (void)launch_k(bn_partial_kernel<false>, dim3(ncta), dim3(th), sm, st, x, x_ld, static_cast<const __half*>(nullptr), 0,
+                 static_cast<const __half*>(nullptr), 0, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), M,
+                 C, 0, rpc, workspace);
+  bn_reduce_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(workspace, ncta, C, sums);
+  return check_cuda(cudaGetLastError(), "bn_sync_forward_stats");
+}
+int launch_bn_sync_forward_apply(const __half* x, int x_ld, long long M, int C, const double* sums, double count, const float* gamma,
+                                 const float* beta, float eps, float momentum, int abs_gamma, float* running_mean,
+                                 float* running_var, const __half* res, int res_ld, int act, __half* y, int y_ld, float* mean,
+                                 float* rstd, float* scale, float* shift, cudaStream_t st) {
+  if (C % 8 || x_ld % 8 || y_ld % 8 || (res && res_ld % 8) || count < 1.0) { set_error("bn_sync_forward_apply: bad shape"); return -1; }
+  bn_finalize_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, count, gamma, beta, eps, momentum, abs_gamma, running_mean,
+                                                           running_var, mean, rstd, scale, shift);
+  const long long n = M * (C / 8);
+  (void)launch_k(bn_apply_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, x_ld,
+                 static_cast<const float*>(scale), static_cast<const float*>(shift), res, res_ld, act, y, y_ld, M, C);
+  return check_cuda(cudaGetLastError(), "bn_sync_forward_apply");
+}
+int launch_bn_sync_backward_stats(const __half* x, int x_ld, const __half* dy, int dy_ld, const __half* y, int y_ld, long long M,
+                                  int C, const float* mean, const float* rstd, int act, float* workspace, double* sums,
+                                  float* dgamma, float* dbeta, cudaStream_t st) {
+  if (C % 8 || x_ld % 8 || dy_ld % 8 || y_ld % 8 || C > 2048 || M < 1) { set_error("bn_sync_backward_stats: bad shape"); return -1; }
+  long long rpc; int th; size_t sm;
+  const int ncta = bn_grid(M, C, rpc, th, sm);
+  if (ncta < 0 || sm > 64 * 1024) { set_error("bn_sync_backward_stats: C=%d too wide", C); return -1; }
+  (void)launch_k(bn_partial_kernel<true>, dim3(ncta), dim3(th), sm, st, x, x_ld, dy, dy_ld, y, y_ld, mean, rstd, M, C, act, rpc,
+                 workspace);
+  bn_reduce_kernel<<<(C * 32 + 127) / 128, 128, 0, st>>>(workspace, ncta, C, sums);
+  bn_bwd_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, nullptr, nullptr, dgamma, dbeta);      // local parameter gradients
+  return check_cuda(cudaGetLastError(), "bn_sync_backward_stats");
+}
+int launch_bn_sync_backward_apply(const __half* x, int x_ld, const __half* dy, int dy_ld, const __half* y, int y_ld, long long M,
+                                  int C, const float* mean, const float* rstd, const float* scale, const double* sums, double count,
+                                  int act, __half* dx, int dx_ld, __half* dres, int dres_ld, float* workspace, cudaStream_t st) {
+  if (C % 8 || x_ld % 8 || dy_ld % 8 || y_ld % 8 || dx_ld % 8 || (dres && dres_ld % 8) || count < 1.0) {
+    set_error("bn_sync_backward_apply: bad shape");
+    return -1;
+  }
+  float* fs = workspace;                                            // [2][C] float copies of the global sums
+  bn_bwd_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, fs, fs + C, nullptr, nullptr);
+  const long long n = M * (C / 8);
+  (void)launch_k(bn_bwd_apply_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, x_ld, dy, dy_ld, y, y_ld,
+                 mean, rstd, scale, static_cast<const float*>(fs), static_cast<const float*>(fs + C), act, dx, dx_ld, dres,
+                 dres_ld, M, C, count);
+  return check_cuda(cudaGetLastError(), "bn_sync_backward_apply");
 }
 
 }  // namespace mf

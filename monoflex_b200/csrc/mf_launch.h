@@ -77,6 +77,18 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
 int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                             __half* out, cudaStream_t st);
+// SyncBatchNorm halves (mf_bn_train.cu)
+int launch_bn_sync_forward_stats(const __half* x, int x_ld, long long M, int C, float* workspace, double* sums, cudaStream_t st);
+int launch_bn_sync_forward_apply(const __half* x, int x_ld, long long M, int C, const double* sums, double count, const float* gamma,
+                                 const float* beta, float eps, float momentum, int abs_gamma, float* running_mean,
+                                 float* running_var, const __half* res, int res_ld, int act, __half* y, int y_ld, float* mean,
+                                 float* rstd, float* scale, float* shift, cudaStream_t st);
+int launch_bn_sync_backward_stats(const __half* x, int x_ld, const __half* dy, int dy_ld, const __half* y, int y_ld, long long M,
+                                  int C, const float* mean, const float* rstd, int act, float* workspace, double* sums,
+                                  float* dgamma, float* dbeta, cudaStream_t st);
+int launch_bn_sync_backward_apply(const __half* x, int x_ld, const __half* dy, int dy_ld, const __half* y, int y_ld, long long M,
+                                  int C, const float* mean, const float* rstd, const float* scale, const double* sums, double count,
+                                  int act, __half* dx, int dx_ld, __half* dres, int dres_ld, float* workspace, cudaStream_t st);
 // GPU input pipeline (mf_input.cu)
 int launch_preprocess_u8(const unsigned char* const* src, const int* hw, const int* flip, int B, int H, int W,
                          const float* mean3, const float* std3, int to_bgr, float* out, cudaStream_t st);

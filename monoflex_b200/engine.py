@@ -269,6 +269,24 @@ class Plan(object):
                 self.bn_saved.append((mod, raw, y, stats, c0, cc))
                 momentum = getattr(mod, "momentum", 0.1)
                 eps = getattr(mod, "eps", BN_EPS)
+                group, world = sync_bn_group(mod)
+                if world > 1:
+                    # torch.nn.SyncBatchNorm (the reference's convert_sync_batchnorm, tools/plain_train_net.py:131-132): local sums
+                    # -> all-reduce of 2C doubles -> normalise with the statistics of the GLOBAL batch (csrc/mf_bn_train.cu)
+                    import torch.distributed as dist
+                    sums = torch.zeros(2 * cc, dtype=torch.float64, device=self.device)
+                    self.keep.append(sums)
+                    count = float(raw.M) * world
+                    self.add("mf_bn_sync_forward_stats", lambda c0=c0, cc=cc, ws=ws, sums=sums: (
+                        raw.ptr() + 2 * c0, raw.ld, raw.M, cc, ws.data_ptr(), sums.data_ptr()))
+                    self.add_py(lambda sums=sums, group=group: dist.all_reduce(sums, group=group))
+                    self.add("mf_bn_sync_forward_apply", lambda mod=mod, off=off, c0=c0, cc=cc, stats=stats, sums=sums, momentum=momentum, eps=eps, count=count: (
+                        raw.ptr() + 2 * c0, raw.ld, raw.M, cc, sums.data_ptr(), count, mod.weight.data_ptr() + 4 * off,
+                        mod.bias.data_ptr() + 4 * off, eps, momentum, 1 if abs_weight else 0, mod.running_mean.data_ptr() + 4 * off,
+                        mod.running_var.data_ptr() + 4 * off, (residual.ptr() + 2 * c0) if residual is not None else None,
+                        residual.ld if residual is not None else 0, act, y.ptr() + 2 * c0, y.ld, stats[0].data_ptr(),
+                        stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr()))
+                    continue
                 self.add("mf_bn_train_forward", lambda mod=mod, off=off, c0=c0, cc=cc, stats=stats, ws=ws, momentum=momentum, eps=eps: (
                     raw.ptr() + 2 * c0, raw.ld, raw.M, cc, mod.weight.data_ptr() + 4 * off, mod.bias.data_ptr() + 4 * off, eps,
                     momentum, 1 if abs_weight else 0, mod.running_mean.data_ptr() + 4 * off, mod.running_var.data_ptr() + 4 * off,
@@ -449,6 +467,33 @@ class Plan(object):
         if self.train:
             self.tape.append(dict(kind="upsample_add", x=x, weight=up_weight, wt=wt, skip=skip, f=f, y=y))
         return y
+
+
+def sync_bn_group(mod):
+    """(process group, world size) when `mod` is a torch.nn.SyncBatchNorm in an initialised multi-rank job, else (None, 1)"""
+    import torch.distributed as dist
+    if isinstance(mod, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
+        group = getattr(mod, "process_group", None)
+        return group, dist.get_world_size(group)
+    return None, 1
+
+
+def bn_backward_launch(mod, x_ptr, x_ld, dy_ptr, dy_ld, y_ptr, y_ld, M, cc, stats, act, dx_ptr, dx_ld, dres_ptr, dres_ld, dg, ws,
+                       stream):
+    """mf_bn_train_backward, or its SyncBatchNorm form (local sums -> all-reduce -> apply with the global count) when `mod` is a
+    converted SyncBatchNorm. dg: fp32 [2, cc] (dgamma, dbeta - LOCAL sums in both cases: DDP averages parameter gradients)."""
+    group, world = sync_bn_group(mod)
+    if world > 1:
+        import torch.distributed as dist
+        sums = torch.empty(2 * cc, dtype=torch.float64, device=dg.device)
+        _lib.call("mf_bn_sync_backward_stats", x_ptr, x_ld, dy_ptr, dy_ld, y_ptr, y_ld, M, cc, stats[0].data_ptr(), stats[1].data_ptr(),
+                  act, ws.data_ptr(), sums.data_ptr(), dg[0].data_ptr(), dg[1].data_ptr(), stream)
+        dist.all_reduce(sums, group=group)
+        _lib.call("mf_bn_sync_backward_apply", x_ptr, x_ld, dy_ptr, dy_ld, y_ptr, y_ld, M, cc, stats[0].data_ptr(), stats[1].data_ptr(),
+                  stats[2].data_ptr(), sums.data_ptr(), float(M) * world, act, dx_ptr, dx_ld, dres_ptr, dres_ld, ws.data_ptr(), stream)
+        return
+    _lib.call("mf_bn_train_backward", x_ptr, x_ld, dy_ptr, dy_ld, y_ptr, y_ld, M, cc, stats[0].data_ptr(), stats[1].data_ptr(),
+              stats[2].data_ptr(), act, dx_ptr, dx_ld, dres_ptr, dres_ld, dg[0].data_ptr(), dg[1].data_ptr(), ws.data_ptr(), stream)
 
 
 def fingerprint(module, versions=True):

@@ -16,14 +16,14 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _bn_backward(entry, dy_ptr, dy_ld, dx_ptr, dx_ld, act, M, dev):
-    """mf_bn_train_backward on one <= 256-channel slice kept by Plan.bn_train -> (dgamma, dbeta)."""
+def _bn_backward(entry, dy_ptr, dy_ld, dx_ptr, dx_ld, act, M, dev, mod=None):
+    """mf_bn_train_backward on one <= 256-channel slice kept by Plan.bn_train -> (dgamma, dbeta). `mod`: the normalisation module
+    (a converted torch.nn.SyncBatchNorm exchanges its sums across ranks, engine.bn_backward_launch)."""
     raw, y, stats, c0, cc = entry
     dg = torch.empty(2, cc, dtype=torch.float32, device=dev)
     ws = torch.empty(max(1, load().mf_bn_train_workspace(M, cc) // 4), dtype=torch.float32, device=dev)
-    call("mf_bn_train_backward", raw.ptr() + 2 * c0, raw.ld, dy_ptr, dy_ld, y.ptr() + 2 * c0, y.ld, M, cc, stats[0].data_ptr(),
-         stats[1].data_ptr(), stats[2].data_ptr(), act, dx_ptr, dx_ld, None, 0, dg[0].data_ptr(), dg[1].data_ptr(), ws.data_ptr(),
-         _st())
+    engine.bn_backward_launch(mod, raw.ptr() + 2 * c0, raw.ld, dy_ptr, dy_ld, y.ptr() + 2 * c0, y.ld, M, cc, stats, act, dx_ptr, dx_ld,
+                              None, 0, dg, ws, _st())
     return dg[0], dg[1]
 
 
@@ -99,7 +99,7 @@ def predictor_backward(pred, plan, grad_cls, grad_reg):
             put(seq[3].weight, dw2)
             put(seq[3].bias, db2)
             d_raw = torch.empty(B * K, hc, dtype=torch.half, device=dev)
-            dgam, dbet = _bn_backward(entry, d_t.data_ptr(), hc, d_raw.data_ptr(), hc, 0, B * K, dev)
+            dgam, dbet = _bn_backward(entry, d_t.data_ptr(), hc, d_raw.data_ptr(), hc, 0, B * K, dev, mod=seq[1])
             put(seq[1].weight, dgam)
             put(seq[1].bias, dbet)
             dw1 = torch.empty(hc, hc, 1, 3, dtype=torch.float32, device=dev)

@@ -63,10 +63,10 @@ def _bn_backward(rec_bn, raw, y, dy_ptr, dy_ld, d_raw, d_res, act, abs_weight, p
     for (mod, _raw, _y, stats, c0, cc) in rec_bn:
         dg = torch.empty(2, cc, dtype=torch.float32, device=dev)
         ws = torch.empty(max(1, load().mf_bn_train_workspace(M, cc) // 4), dtype=torch.float32, device=dev)
-        call("mf_bn_train_backward", raw.ptr() + 2 * c0, raw.ld, dy_ptr + 2 * c0, dy_ld, y.ptr() + 2 * c0, y.ld, M, cc,
-             stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), act, d_raw.data_ptr() + 2 * c0, d_raw.shape[1],
-             (d_res.data_ptr() + 2 * c0) if d_res is not None else None, d_res.shape[1] if d_res is not None else 0,
-             dg[0].data_ptr(), dg[1].data_ptr(), ws.data_ptr(), _st())
+        engine.bn_backward_launch(mod, raw.ptr() + 2 * c0, raw.ld, dy_ptr + 2 * c0, dy_ld, y.ptr() + 2 * c0, y.ld, M, cc, stats, act,
+                                  d_raw.data_ptr() + 2 * c0, d_raw.shape[1],
+                                  (d_res.data_ptr() + 2 * c0) if d_res is not None else None,
+                                  d_res.shape[1] if d_res is not None else 0, dg, ws, _st())
         off = c0 - rec_bn[0][4]                                   # slices of one module are consecutive 256-channel chunks
         put(mod.weight, dg[0] * torch.sign(mod.weight.detach()[off:off + cc]) if abs_weight else dg[0], off, cc)
         put(mod.bias, dg[1], off, cc)

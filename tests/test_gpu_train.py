@@ -221,6 +221,23 @@ def test_fused_gradient_exchange_multi_gpu():
     assert '"ok": true' in r.stdout
 
 
+def test_sync_batchnorm_two_ranks_match_two_image_batch():
+    """world >= 2 only (skipped on a 1-GPU box): after the reference's `SyncBatchNorm.convert_sync_batchnorm(model)` the train-mode
+    backbone on one image per rank reproduces the two-image single-process forward (global batch statistics), its running
+    statistics and - summed over ranks - its parameter gradients (tools/syncbn_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "syncbn_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"ok": true' in r.stdout
+
+
 # ------------------------------------------------------------------------------------------------ conv backward building blocks
 @pytest.mark.parametrize("case", [
     # B, H, W, Cin, Cout, k, stride, pad
@@ -341,6 +358,76 @@ def _rows_of(t4):
 
 def _nchw_of(rows, B, H, W):
     return rows.float().cpu().view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("case", [(4096, 64, 1, True), (3000, 16, 1, False), (2048, 256, 2, False)])
+def test_sync_batchnorm_halves_equal_fused_kernels(case):
+    """SyncBatchNorm kernels (mf_bn_sync_*) with the exchange SIMULATED on one GPU: the rows of a tensor are split between two
+    "ranks", each computes its local sums, the sums are added (what the NCCL all-reduce does) and each half is normalised /
+    back-propagated with the global count - the result must equal the single-call mf_bn_train_forward / _backward on the whole
+    tensor (same arithmetic, different partial-sum grouping), including running statistics, dgamma and dbeta (summed over ranks)."""
+    from monoflex_b200._lib import call, load, stream
+    M, C, act, with_res = case
+    gen = np.random.Generator(np.random.PCG64(M + C))
+    dev = "cuda"
+    x = torch.from_numpy((gen.standard_normal((M, C)) * 1.5 + 0.3).astype(np.float32)).half().to(dev)
+    dy = torch.from_numpy((gen.standard_normal((M, C)) * 0.2).astype(np.float32)).half().to(dev)
+    res = torch.from_numpy(gen.standard_normal((M, C)).astype(np.float32)).half().to(dev) if with_res else None
+    gamma = torch.from_numpy(gen.uniform(0.5, 1.5, C).astype(np.float32)).to(dev)
+    beta = torch.from_numpy((gen.standard_normal(C) * 0.1).astype(np.float32)).to(dev)
+    st = stream()
+
+    def ws_for(m):
+        return torch.empty(load().mf_bn_train_workspace(m, C) // 4, dtype=torch.float32, device=dev)
+
+    # ---- fused reference on the whole tensor
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    y = torch.empty_like(x)
+    stats = torch.empty(4, C, dtype=torch.float32, device=dev)
+    ws = ws_for(M)
+    call("mf_bn_train_forward", x.data_ptr(), C, M, C, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, 0, rm.data_ptr(), rv.data_ptr(),
+         res.data_ptr() if with_res else None, C, act, y.data_ptr(), C, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+         stats[3].data_ptr(), ws.data_ptr(), st)
+    dx, dres = torch.empty_like(x), (torch.empty_like(x) if with_res else None)
+    dg = torch.empty(2, C, dtype=torch.float32, device=dev)
+    call("mf_bn_train_backward", x.data_ptr(), C, dy.data_ptr(), C, y.data_ptr(), C, M, C, stats[0].data_ptr(), stats[1].data_ptr(),
+         stats[2].data_ptr(), act, dx.data_ptr(), C, dres.data_ptr() if with_res else None, C, dg[0].data_ptr(), dg[1].data_ptr(),
+         ws.data_ptr(), st)
+    # ---- two simulated ranks
+    split = (M * 3 // 8) // 8 * 8
+    parts = [(0, split), (split, M)]
+    sums = [torch.zeros(2 * C, dtype=torch.float64, device=dev) for _ in parts]
+    for (lo, hi), sm in zip(parts, sums):
+        call("mf_bn_sync_forward_stats", x[lo:hi].data_ptr(), C, hi - lo, C, ws_for(hi - lo).data_ptr(), sm.data_ptr(), st)
+    total = sums[0] + sums[1]                                             # the all-reduce
+    y2 = torch.empty_like(x)
+    st2 = [torch.empty(4, C, dtype=torch.float32, device=dev) for _ in parts]
+    rms = [(torch.zeros(C, device=dev), torch.ones(C, device=dev)) for _ in parts]
+    for (lo, hi), s4, (rm2, rv2) in zip(parts, st2, rms):
+        call("mf_bn_sync_forward_apply", x[lo:hi].data_ptr(), C, hi - lo, C, total.data_ptr(), float(M), gamma.data_ptr(), beta.data_ptr(),
+             1e-5, 0.1, 0, rm2.data_ptr(), rv2.data_ptr(), res[lo:hi].data_ptr() if with_res else None, C, act, y2[lo:hi].data_ptr(), C,
+             s4[0].data_ptr(), s4[1].data_ptr(), s4[2].data_ptr(), s4[3].data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y) or (y2.float() - y.float()).abs().max().item() <= 2e-3 * y.float().abs().max().item()
+    for s4, (rm2, rv2) in zip(st2, rms):
+        assert (s4 - stats).abs().max().item() <= 1e-5 * stats.abs().max().item()
+        assert (rm2 - rm).abs().max().item() <= 1e-6 and (rv2 - rv).abs().max().item() <= 1e-6
+    bs = [torch.zeros(2 * C, dtype=torch.float64, device=dev) for _ in parts]
+    dgs = [torch.empty(2, C, dtype=torch.float32, device=dev) for _ in parts]
+    for (lo, hi), sm, d2 in zip(parts, bs, dgs):
+        call("mf_bn_sync_backward_stats", x[lo:hi].data_ptr(), C, dy[lo:hi].data_ptr(), C, y[lo:hi].data_ptr(), C, hi - lo, C,
+             stats[0].data_ptr(), stats[1].data_ptr(), act, ws_for(hi - lo).data_ptr(), sm.data_ptr(), d2[0].data_ptr(), d2[1].data_ptr(), st)
+    btot = bs[0] + bs[1]
+    dx2, dres2 = torch.empty_like(x), (torch.empty_like(x) if with_res else None)
+    for (lo, hi) in parts:
+        call("mf_bn_sync_backward_apply", x[lo:hi].data_ptr(), C, dy[lo:hi].data_ptr(), C, y[lo:hi].data_ptr(), C, hi - lo, C,
+             stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), btot.data_ptr(), float(M), act, dx2[lo:hi].data_ptr(), C,
+             dres2[lo:hi].data_ptr() if with_res else None, C, ws_for(hi - lo).data_ptr(), st)
+    torch.cuda.synchronize()
+    assert (dx2.float() - dx.float()).abs().max().item() <= 2e-3 * dx.float().abs().max().item()
+    if with_res:
+        assert torch.equal(dres2, dres)
+    assert ((dgs[0] + dgs[1]) - dg).abs().max().item() <= 1e-4 * dg.abs().max().item()
 
 
 def test_conv_dgrad_stride2_parity_decomposition():
