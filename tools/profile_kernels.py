@@ -1,4 +1,4 @@
-"""ncu driver: replays selected launches of the B=8 inference plan between cudaProfilerStart/Stop.
+"""ncu driver: replays selected launches of the B=8 inference plan (MF_PRECISION = strict | fast) between cudaProfilerStart/Stop.
    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python tools/profile_kernels.py
 Selected: the head 3x3 implicit GEMM (N=2304), one 64->64 DCN (+ its offset conv) at 96x320, a level-3 3x3 conv,
 the stem 7x7, an up-sample+add, and the two decode kernels."""
@@ -34,17 +34,33 @@ def pick(plan, name, pred):
     raise KeyError(name)
 
 
-sel_spec = [
-    ("head", hp, "mf_head_fused", lambda a: True),
-    ("dcn64", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 64 and a[3] == 96),
-    ("dcn128", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 128 and a[3] == 48),
-    ("offconv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 27 and a[5] == 64 and a[3] == 96),
-    ("conv128", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 128 and a[5] == 128 and a[9] == 3),
-    ("conv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 64 and a[5] == 64 and a[9] == 3),
-    ("stem", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 8),
-    ("level0", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 16 and a[5] == 1),
-    ("upadd", bp, "mf_upsample_add_nhwc_f16", lambda a: a[6] == 160),
-]
+if model.precision == "strict":
+    # strict precision: pair kernels (argument lists of engine.py's x2 emitters)
+    sel_spec = [
+        ("head", hp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 2304),
+        ("head_1x1", hp, "mf_conv2d_nhwc_f16x2", lambda a: a[10] == 1 and a[14] == 20),
+        ("dcn64", bp, "mf_dcn_nhwc_f16x2", lambda a: a[6] == 64 and a[4] == 96),
+        ("dcn128", bp, "mf_dcn_nhwc_f16x2", lambda a: a[6] == 128 and a[4] == 48),
+        ("offconv64", bp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 27 and a[6] == 64 and a[4] == 96),
+        ("conv128", bp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 128 and a[6] == 128 and a[10] == 3),
+        ("conv64", bp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 64 and a[6] == 64 and a[10] == 3),
+        ("conv512", bp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 512 and a[6] == 512 and a[10] == 3),
+        ("stem", bp, "mf_conv2d_rows_f16x2", lambda a: a[4] == 8),
+        ("level0", bp, "mf_conv2d_rows_f16x2", lambda a: a[4] == 16),
+        ("upadd", bp, "mf_upsample_add_split", lambda a: a[10] == 160),
+    ]
+else:
+    sel_spec = [
+        ("head", hp, "mf_head_fused", lambda a: True),
+        ("dcn64", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 64 and a[3] == 96),
+        ("dcn128", bp, "mf_dcn_nhwc_f16", lambda a: a[5] == 128 and a[3] == 48),
+        ("offconv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 27 and a[5] == 64 and a[3] == 96),
+        ("conv128", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 128 and a[5] == 128 and a[9] == 3),
+        ("conv64", bp, "mf_conv2d_nhwc_f16", lambda a: a[13] == 64 and a[5] == 64 and a[9] == 3),
+        ("stem", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 8),
+        ("level0", bp, "mf_conv2d_rows_f16", lambda a: a[4] == 16 and a[5] == 1),
+        ("upadd", bp, "mf_upsample_add_nhwc_f16", lambda a: a[6] == 160),
+    ]
 only = os.environ.get("ONLY")
 sel = [(n, pick(pl, k, pred)) for n, pl, k, pred in sel_spec if not only or n in only.split(",")]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
