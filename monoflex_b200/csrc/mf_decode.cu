@@ -345,7 +345,22 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
                   const float* dim_mean, int B, int C, int H, int W, int R, int K, float thresh, int apply_sigmoid,
                   float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
                   float* pois, float* result, int* count, cudaStream_t st) {
-  const int S = MF_DECODE_SLABS;
+  // slabs per (image, class) plane: more slabs = shorter per-CTA scans but more CTAs; one CTA of 1024 threads per SM, so a second
+  // wave doubles the kernel (the fixed S = 8 of round 1 put 192 CTAs on 148 SMs at B = 8). Pick the S <= 8 that minimises
+  // waves x (items per thread + the ~6 items' worth of radix-pass overhead).
+  int S = 1, best = 1 << 30, nsm_dec = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm_dec, cudaDevAttrMultiProcessorCount, dev);
+    for (int s = 1; s <= MF_DECODE_SLABS; ++s) {
+      if (C * s * K > S2_KEYS) break;
+      const int waves = (B * C * s + nsm_dec - 1) / nsm_dec;
+      const int items = ((H * W + s - 1) / s + S1_THREADS - 1) / S1_THREADS;
+      const int cost = waves * (items + 6);
+      if (cost < best) { best = cost; S = s; }
+    }
+  }
   if (H * W > 32768 || C > 3 || C * S * K > S2_KEYS || K > 64 || R != 50) {
     set_error("decode: unsupported shape H*W=%d C=%d K=%d R=%d", H * W, C, K, R);
     return -1;

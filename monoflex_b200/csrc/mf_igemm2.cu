@@ -429,7 +429,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           // strict precision: hi and lo halves of the four corners are blended in fp32 ONCE per (tap, 64-channel chunk) and
           // feed three consecutive K blocks: hi (x W_hi), lo (x W_hi), hi again (x W_lo).
           const int lo_bytes = p.x_lo * 2;
-          for (int kb = 0; kb < nkb; kb += 3) {
+          for (int kb = 0; kb < nkb; kb += (p.pair ? 2 : 3)) {
             const char* xb = x_img + c0 * 2;
             const uint32_t rec = (tap * BM + rsub) * 16;
             uint4 hi4[PASSES], lo4[PASSES];
@@ -468,6 +468,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             }
 #pragma unroll
             for (int which = 0; which < 3; ++which) {
+              if (which == 2 && p.pair) break;               // pair schedule: the MMA warp re-uses the hi stage for A_hi W_lo
               mbar_wait(&empty_bar[stage], phase ^ 1);
               const uint32_t a_stage = smem_u32(a_smem + stage * A_STAGE);
 #pragma unroll
@@ -568,7 +569,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               tma_load_im2col_4d(a_dst + jb * box_bytes, &tmap_x, &full_bar[stage],
                                  valid ? c0 + (which == 1 ? p.x_lo : 0) : p.Cin, cw, chh, cn,
                                  static_cast<uint16_t>(valid ? kx : 0), static_cast<uint16_t>(valid ? ky : 0));
-              if (p.split_in && ++which < 3) continue;
+              if (p.split_in && ++which < (p.pair ? 2 : 3)) continue;
               which = 0;
               c0 += kc;
               if (c0 >= p.Cin) {
@@ -577,7 +578,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               }
             }
           }
-          tma_load_2d(smem_u32(b_smem + stage * B_STAGE), &tmap_w, &full_bar[stage], kb * BK, n0);
+          // weight K coordinate: plain / K-concatenation = K block kb; pair schedule = block 3*(kb/2) (W_hi) for the hi stage
+          // and 3*(kb/2)+2 (W_lo) for the lo stage of the same (tap, chunk)
+          const int wk = p.pair ? (3 * (kb >> 1) + ((kb & 1) << 1)) : kb;
+          tma_load_2d(smem_u32(b_smem + stage * B_STAGE), &tmap_w, &full_bar[stage], wk * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -608,6 +612,32 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         mbar_wait(&acc_empty[acc], ((ti >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+        if (p.pair) {
+          // pair schedule: stage s0 = (A_hi, W_hi), stage s1 = (A_lo, W_lo) of one (tap, 64-channel chunk); three products
+          for (int kb = 0; kb < nkb; kb += 2) {
+            const int s0 = stage;
+            mbar_wait(&full_bar[s0], phase);
+            tc_fence_after();
+            const uint64_t a0 = static_cast<uint64_t>((s0 * A_STAGE) >> 4), b0s = static_cast<uint64_t>((s0 * B_STAGE) >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4)                                     // A_hi W_hi
+              umma_f16(d_tmem, a_d0[k4] + a0, b_d0 + b0s + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            const int s1 = stage;
+            mbar_wait(&full_bar[s1], phase);
+            tc_fence_after();
+            const uint64_t a1 = static_cast<uint64_t>((s1 * A_STAGE) >> 4), b1s = static_cast<uint64_t>((s1 * B_STAGE) >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4)                                     // A_lo W_hi
+              umma_f16(d_tmem, a_d0[k4] + a1, b_d0 + b0s + 2 * k4, idesc, 1u);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4)                                     // A_hi W_lo
+              umma_f16(d_tmem, a_d0[k4] + a0, b_d0 + b1s + 2 * k4, idesc, 1u);
+            umma_commit(&empty_bar[s0]);
+            umma_commit(&empty_bar[s1]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int kb = 0; kb < nkb; ++kb) {
           if (A_STAT && inner == 0) mbar_wait(&a_full[kb], mi & 1);   // resident A block of this m-tile has landed
           mbar_wait(&full_bar[stage], phase);
@@ -797,6 +827,10 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d) kc=%d", static_cast<int>(r), kc); return -1; }
     a_tma = true;
     pp.kc = kc;
+  }
+  if (p.split_in && g_tunable[11] == 0 && (mode == MODE_DCN || (a_tma && kc == 64))) {
+    pp.pair = 1;                                                   // see IgemmParams::pair
+    pp.nkb = 2 * p.kh * p.kw * (p.Cin / 64);
   }
   const int ntn_host = (p.Cout + bn - 1) / bn;
   if (p.split_out && use_tma_store) {          // staged hi/lo tiles: the SPLIT instantiations (N tiles of 64 / 128 only)

@@ -40,6 +40,11 @@ struct IgemmParams {
   int split_in, split_out;
   int x_lo, res_lo, y_lo;
   int cw;       // split_in: channels per chunk = min(Cin, 64)
+  // pair schedule (set by launch_igemm2 for split_in with 64-channel K blocks): per (tap, chunk) only TWO stages are filled,
+  // (A_hi, W_hi) and (A_lo, W_lo), and the MMA warp issues the three products A_hi W_hi, A_lo W_hi, A_hi W_lo across them -
+  // one third less operand traffic into shared memory than the K-concatenation (which loads A_hi and W_hi twice).
+  // nkb then counts stage fills = 2 * taps * Cin / 64.
+  int pair;
 };
 
 int igemm_block_n(int cout);
