@@ -447,20 +447,28 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               vl[2] = __ldg(reinterpret_cast<const uint4*>(xb + o.z + lo_bytes));
               vl[3] = __ldg(reinterpret_cast<const uint4*>(xb + o.w + lo_bytes));
               const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+              // the lo halves are 2^-11 of the value: their blend needs 11 bits only and runs in packed fp16 (HFMA2, no
+              // conversions, error 2^-22 of the value); the hi halves are blended in fp32 with the fp32 weights
+              __half2 wh2[4];
+#pragma unroll
+              for (int cn = 0; cn < 4; ++cn) wh2[cn] = __float2half2_rn(wv[cn]);
               __half2* oh = reinterpret_cast<__half2*>(&hi4[q]);
               __half2* ol = reinterpret_cast<__half2*>(&lo4[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 unsigned long long acc = f2_pack(0.f, 0.f);
+                __half2 lacc = __hmul2(wh2[0], reinterpret_cast<const __half2*>(&vl[0])[e]);
 #pragma unroll
                 for (int cn = 0; cn < 4; ++cn) {
                   const float2 fh = __half22float2(reinterpret_cast<const __half2*>(&vh[cn])[e]);
-                  const float2 fl = __half22float2(reinterpret_cast<const __half2*>(&vl[cn])[e]);
                   const unsigned long long w2 = f2_pack(wv[cn], wv[cn]);
                   acc = f2_fma(w2, f2_pack(fh.x, fh.y), acc);
-                  acc = f2_fma(w2, f2_pack(fl.x, fl.y), acc);
+                  if (cn > 0) lacc = __hfma2(wh2[cn], reinterpret_cast<const __half2*>(&vl[cn])[e], lacc);
                 }
-                const float2 r2 = f2_unpack(acc);
+                float2 r2 = f2_unpack(acc);
+                const float2 lf = __half22float2(lacc);
+                r2.x += lf.x;
+                r2.y += lf.y;
                 oh[e] = __floats2half2_rn(r2.x, r2.y);
                 const float2 hf = __half22float2(oh[e]);
                 ol[e] = __floats2half2_rn(r2.x - hf.x, r2.y - hf.y);
