@@ -46,6 +46,34 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, i
   return check_cuda(cudaGetLastError(), "pack_conv_weight");
 }
 
+// batched form for training plans: all weights of a plan are re-packed from their live fp32 parameters at the start of every
+// run - one launch over a device table of descriptors instead of ~190 small ones. desc (5 x int64): w ptr, out ptr,
+// Cout | Cin << 32, taps | cin_pad << 32, n_pad | k_pad << 32.
+__global__ void pack_conv_weight_batched_kernel(const long long* __restrict__ descs, int n) {
+  const int d = blockIdx.y;
+  if (d >= n) return;
+  const long long* q = descs + 5 * d;
+  const float* w = reinterpret_cast<const float*>(q[0]);
+  __half* out = reinterpret_cast<__half*>(q[1]);
+  const int Cout = static_cast<int>(q[2] & 0xffffffffll), Cin = static_cast<int>(q[2] >> 32);
+  const int taps = static_cast<int>(q[3] & 0xffffffffll), cin_pad = static_cast<int>(q[3] >> 32);
+  const int n_pad = static_cast<int>(q[4] & 0xffffffffll), k_pad = static_cast<int>(q[4] >> 32);
+  const long long total = static_cast<long long>(n_pad) * k_pad;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % k_pad), nn = static_cast<int>(i / k_pad);
+    const int tap = k / cin_pad, c = k - tap * cin_pad;
+    float v = 0.f;
+    if (nn < Cout && tap < taps && c < Cin) v = w[(static_cast<long long>(nn) * Cin + c) * taps + tap];
+    out[i] = __float2half_rn(v);
+  }
+}
+int launch_pack_conv_weight_batched(const long long* descs, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  pack_conv_weight_batched_kernel<<<dim3(64, n), 256, 0, st>>>(descs, n);
+  return check_cuda(cudaGetLastError(), "pack_conv_weight_batched");
+}
+
 // boundary B (exact-fp32 `_ext.dcn_v2_forward/backward` on NCHW tensors): kernels and launchers live in mf_dcn_f32.cu
 
 int g_tunable[16] = {0};   // experiment switches, see mf_set_tunable in include/monoflex_b200.h
@@ -87,6 +115,10 @@ int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, 
                         void* out_f16, void* stream) {
   return launch_pack_conv_weight(w_oihw, Cout, Cin, kh, kw, cin_pad, n_pad, k_pad, static_cast<__half*>(out_f16),
                                  MF_STREAM(stream));
+}
+
+int mf_pack_conv_weights_batched(const void* descs_dev, int n, void* stream) {
+  return launch_pack_conv_weight_batched(static_cast<const long long*>(descs_dev), n, MF_STREAM(stream));
 }
 
 int mf_conv2d_nhwc_f16(const void* x, int x_ld, int B, int H, int W, int Cin, const void* w_packed, int n_pad, int k_pad,

@@ -100,6 +100,7 @@ class Plan(object):
         self.keep = []       # tensors that must outlive the plan (packed weights, scale/shift, ...)
         self.launches = []   # (fn, args) after finalize
         self.n_launch = 0
+        self.pack_descs = [] # train mode: (src fp32 tensor, dst ptr, cout, cin, taps, cin_pad, n_pad, k_pad) re-packed on every run
 
     # ---- symbolic construction
     def act(self, B, H, W, C, split=None):
@@ -146,6 +147,15 @@ class Plan(object):
                 a.buf, a.ch_off = root.buf, off
                 a.owner = None
         lib = _lib.load()
+        if self.pack_descs:
+            # ONE batched re-pack of every weight from its live parameter at the start of each run (weights only change between
+            # runs); descriptor table on the device, see mf_pack_conv_weights_batched
+            rows = [[src.data_ptr(), dst, cout | (cin << 32), taps | (cin_pad << 32), n_pad | (k_pad << 32)]
+                    for (src, dst, cout, cin, taps, cin_pad, n_pad, k_pad) in self.pack_descs]
+            table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self.keep.append(table)
+            n_desc = len(rows)
+            self.launches.append((lib.mf_pack_conv_weights_batched, (table.data_ptr(), n_desc), "mf_pack_conv_weights_batched"))
         for fn_name, argbuilder in self.ops:
             if fn_name == "__py__":
                 self.launches.append((argbuilder, None, fn_name))
@@ -197,8 +207,8 @@ class Plan(object):
             self.keep.append(out)
             row = 0
             for t in parts:
-                self.add("mf_pack_conv_weight", lambda t=t, row=row: (t.data_ptr(), t.shape[0], cin, kh, kw, cin, t.shape[0], k_pad,
-                                                                        out.data_ptr() + 2 * row * k_pad))
+                self.keep.append(t)
+                self.pack_descs.append((t, out.data_ptr() + 2 * row * k_pad, t.shape[0], cin, kh * kw, cin, t.shape[0], k_pad))
                 row += t.shape[0]
             return out, cout, k_pad
         live = self.train and w.dtype == torch.float32 and w.is_contiguous()
@@ -222,7 +232,7 @@ class Plan(object):
             # train mode: `w` aliases the parameter's storage (the optimiser updates it in place), so the repack is a plan op
             # executed on every run instead of once at build time - the plan itself stays valid across optimiser steps
             self.keep.append(w)
-            self.add("mf_pack_conv_weight", lambda: (w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr()))
+            self.pack_descs.append((w, out.data_ptr(), cout, cin, kh * kw, cin_pad, n_pad, k_pad))
         else:
             assert not self.train or not w.requires_grad
             _lib.call("mf_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, cin_pad, n_pad, k_pad, out.data_ptr(),
