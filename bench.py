@@ -233,6 +233,9 @@ def launch_flops(name, a):
     if name == "mf_dcn_nhwc_f16x2":
         _, _, _, b_, h_, w_, cin = a[:7]
         return 2.0 * b_ * h_ * w_ * a[12] * 9 * cin
+    if name == "mf_head_conv_f16x2":     # strict: nbranch x (3x3 Cin->256) with the 1x1 heads (ntot outputs) in the epilogue
+        _, _, _, b_, h_, w_, cin = a[:7]
+        return 2.0 * b_ * h_ * w_ * (a[10] * 256 * 9 * cin + a[16] * 256)
     return 0.0
 
 
@@ -242,8 +245,10 @@ def launch_group(name, a, plan_kind):
         return "stem"
     if name in ("mf_dcn_nhwc_f16", "mf_dcn_nhwc_f16x2"):
         return "dcn"
-    if name == "mf_head_fused":
+    if name in ("mf_head_fused", "mf_head_conv_f16x2"):
         return "head"
+    if name == "mf_head2_reduce":
+        return "head_1x1"
     if name in ("mf_conv2d_nhwc_f16", "mf_conv2d_nhwc_f16x2"):
         x2 = name.endswith("x2")
         cin, kh, cout = (a[6], a[10], a[14]) if x2 else (a[5], a[9], a[13])
@@ -267,8 +272,9 @@ KERNEL_OF_GROUP = {
     "base_convs": "igemm2_kernel<BLOCK_N, MODE_CONV_TMA> (csrc/mf_igemm2.cu): DLA-34 levels 2-5, roots, projects",
     "dcn": "igemm2_kernel<BLOCK_N, MODE_DCN, 16> (csrc/mf_igemm2.cu): fused DCNv2 gather + contraction, 16 layers",
     "offset_convs": "igemm2_kernel<32, MODE_CONV_TMA>: the 16 conv_offset_mask 3x3 convs (27 channels)",
-    "head": "predictor 9 x (3x3 64->256 + IABN): head_fused_kernel (fast) / igemm2_kernel<128, MODE_CONV_TMA, SPLIT> N=2304 (strict)",
-    "head_1x1": "igemm2_kernel<16|32, MODE_CONV_TMA>: the 1x1 output convs on the hi/lo hidden map (strict only)",
+    "head": "predictor 9 x (3x3 64->256 + IABN) + 1x1 heads: head_fused_kernel (fast) / igemm2_kernel<256, MODE_CONV_TMA, 4, HEAD2> "
+            "N=2304 pair GEMM with the 1x1 heads contracted in the epilogue (strict)",
+    "head_1x1": "head2_reduce_kernel: fixed-order sum of the eight partial planes + bias -> cls / reg maps (strict only)",
     "upsample_pool": "upsample_add / maxpool2 (HBM-bound layout kernels)",
     "edge_fusion": "edge gather + Conv1d GEMM + indexed add + sigmoid",
 }

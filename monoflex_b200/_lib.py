@@ -22,6 +22,8 @@ SIGNATURES = {
     "mf_pack_conv_weight_split": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "mf_conv2d_nhwc_f16x2": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I,
                              _I, _I, _P],
+    "mf_head_conv_f16x2": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P],
+    "mf_head2_reduce": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mf_dcn_nhwc_f16x2": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "mf_conv2d_rows_f16x2": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _I, _P],
     "mf_pack_image_pair8": [_P, _P, _I, _I, _I, _I, _P],
@@ -103,7 +105,7 @@ def load():
             fn.argtypes = args
             fn.restype = _SZ if name.endswith("_workspace") else _I
         _lib = lib
-        for i, name in enumerate(("MF_DCN_EXTRA_SMEM", "MF_CONV_EXTRA_SMEM", "MF_UNUSED_2", "MF_NO_TMA_STORE", "MF_NO_TMA_IM2COL", "MF_TMA_SMALL_C", "MF_A_STATIONARY", "MF_DCN_WARPS_MODE", "MF_PDL", "MF_HEAD_CLUSTER", "MF_WGRAD_NO_NARROW", "MF_SPLIT_KCONCAT")):     # experiments only
+        for i, name in enumerate(("MF_DCN_EXTRA_SMEM", "MF_CONV_EXTRA_SMEM", "MF_UNUSED_2", "MF_NO_TMA_STORE", "MF_NO_TMA_IM2COL", "MF_TMA_SMALL_C", "MF_A_STATIONARY", "MF_DCN_WARPS_MODE", "MF_PDL", "MF_HEAD_CLUSTER", "MF_WGRAD_NO_NARROW", "MF_SPLIT_KCONCAT", "MF_HEAD2_BN128")):     # experiments only
             if os.environ.get(name):
                 lib.mf_set_tunable(i, int(os.environ[name]))
         if os.environ.get("MF_CONV_IMPL"):            # diagnostics only: 1 = CUDA-core cross-check kernels

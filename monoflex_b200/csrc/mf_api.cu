@@ -166,6 +166,40 @@ int mf_conv2d_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W,
   if (g_conv_impl == 1) { set_error("mf_conv2d_nhwc_f16x2: no CUDA-core cross-check of the split path"); return -1; }
   return launch_igemm2(p, static_cast<const __half*>(w_packed), n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
 }
+int mf_head_conv_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const void* w_packed, int n_pad, int k_pad,
+                       int nbranch, const float* scale, const float* shift, int act, const float* w2, float* part, int ntot,
+                       const int* out_nch, const int* out_ch0, const int* hid_col, void* hid, int hid_ld, int hid_lo,
+                       const unsigned char* hid_mask, void* stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  if (nbranch <= 0 || nbranch > 12) { set_error("mf_head_conv_f16x2: 1..12 branches"); return -1; }
+  p.x = static_cast<const __half*>(x); p.x_ld = x_ld; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.kh = 3; p.kw = 3; p.stride = 1; p.pad = 1; p.Ho = H; p.Wo = W; p.M = B * H * W;
+  p.split_in = 1; p.split_out = 0; p.x_lo = x_lo; p.cw = 64;
+  p.K_real = 27 * Cin; p.nkb = (p.K_real + 63) / 64;
+  p.Cout = nbranch * 256; p.scale = scale; p.shift = shift; p.act = act;
+  p.out_mode = OUT_F32_NCHW;                     // no output tensor map: the epilogue writes partial planes + masked hidden rows
+  p.y = hid; p.y_ld = hid_ld; p.y_lo = hid_lo;
+  p.h2_w = w2; p.h2_part = part; p.h2_ntot = ntot; p.h2_mask = hid_mask;
+  bool need_hid = false;
+  for (int i = 0; i < nbranch; ++i) {
+    if (out_nch[i] < 0 || out_nch[i] > 32 || out_ch0[i] < 0 || out_ch0[i] + out_nch[i] > ntot) {
+      set_error("mf_head_conv_f16x2: branch %d has %d outputs at %d of %d", i, out_nch[i], out_ch0[i], ntot);
+      return -1;
+    }
+    p.h2_nch[i] = out_nch[i]; p.h2_ch0[i] = out_ch0[i]; p.h2_hid_col[i] = hid_col[i];
+    need_hid = need_hid || hid_col[i] >= 0;
+  }
+  if (need_hid && (hid == nullptr || hid_mask == nullptr || hid_ld % 8 != 0 || hid_lo % 8 != 0)) {
+    set_error("mf_head_conv_f16x2: hidden rows requested without a buffer / mask (or unaligned strides)");
+    return -1;
+  }
+  if (Cin % 64 != 0 || w2 == nullptr || part == nullptr) { set_error("mf_head_conv_f16x2: Cin %% 64, w2 and part are required"); return -1; }
+  return launch_igemm2(p, static_cast<const __half*>(w_packed), n_pad, k_pad, MODE_CONV, MF_STREAM(stream));
+}
+int mf_head2_reduce(const float* part, const float* bias, float* cls, float* reg, int B, int ncls, int nreg, int HW, void* stream) {
+  return launch_head2_reduce(part, bias, cls, reg, B, ncls, nreg, HW, MF_STREAM(stream));
+}
 int mf_dcn_nhwc_f16x2(const void* x, int x_ld, int x_lo, int B, int H, int W, int Cin, const float* offmask, int om_ld,
                       const void* w_packed, int n_pad, int k_pad, int Cout, const float* scale, const float* shift, int act,
                       void* y, int y_ld, int y_lo, void* stream) {

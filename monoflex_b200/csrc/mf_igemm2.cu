@@ -29,17 +29,19 @@ static constexpr int AS_MAX_KB = 9;          // A-stationary mode: at most 9 res
 
 // SPLIT: the fp16 NHWC output is a hi/lo pair (strict-precision mode): two staging tiles per 64-channel sub-tile, paid for
 // with one pipeline stage (the K loop of a split layer is 3x longer, so the shallower ring costs nothing measurable).
-template <int BLOCK_N, int MODE, bool SPLIT = false>
+// EPI (see igemm2_kernel): 1 = SPLIT doubles the staging, 2 = HEAD2 has no output staging at all (256-column tiles fit).
+template <int BLOCK_N, int MODE, int EPI = 0>
 struct Cfg2 {
+  static constexpr bool SPLIT = EPI == 1;
   static constexpr bool A_STAT = MODE == MODE_CONV_TMA_AS;
-  static constexpr int STAGES0 = A_STAT ? 3 : (MODE == MODE_DCN ? 4 : (BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : (BLOCK_N >= 32 ? 5 : 6))));
+  static constexpr int STAGES0 = A_STAT ? 3 : (MODE == MODE_DCN ? 4 : (BLOCK_N >= 256 ? 4 : BLOCK_N >= 128 ? 5 : (BLOCK_N >= 64 ? 6 : (BLOCK_N >= 32 ? 5 : 6))));
   static constexpr int STAGES = (SPLIT && BLOCK_N >= 64) ? ((MODE == MODE_DCN && BLOCK_N < 128) ? STAGES0 : STAGES0 - 1) : STAGES0;
   static constexpr int A_REGION = (A_STAT ? AS_MAX_KB : STAGES) * A_STAGE;
   static constexpr int LAG = BLOCK_N >= 64 ? 3 : (BLOCK_N >= 32 ? 3 : 4);   // cp.async groups in flight per producer thread
   static constexpr int CTAS_PER_SM = BLOCK_N >= 64 ? 1 : 2;
   static constexpr int B_STAGE = BLOCK_N * BK * 2;
   static constexpr int OUT_HALF = BLOCK_N >= 64 ? (BLOCK_N / 64) * A_STAGE : 0;     // staging of one fp16 tile
-  static constexpr int OUT_STAGE = SPLIT ? 2 * OUT_HALF : OUT_HALF;
+  static constexpr int OUT_STAGE = EPI == 2 ? 0 : (SPLIT ? 2 * OUT_HALF : OUT_HALF);
   static constexpr int BAR_BYTES = 256;                         // barriers + tmem ptr
   static constexpr int PRM_BYTES = MODE == MODE_DCN ? 9 * BM * 32 : 0;   // DCN sampling records
   static constexpr int SMEM = A_REGION + STAGES * B_STAGE + OUT_STAGE + BAR_BYTES + 2 * BLOCK_N * 4 + PRM_BYTES + 1024;
@@ -62,14 +64,17 @@ MF_DEVINL void act_chunk(float (&v)[N], int act, int nb) {
   }
 }
 
-template <int BLOCK_N, int MODE, int NPW, bool SPLIT>
-__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE, SPLIT>::CTAS_PER_SM)
+// EPI: 0 = plain epilogue, 1 = SPLIT (staged hi/lo output tiles), 2 = HEAD2 (1x1 head contraction in the epilogue, see IgemmParams)
+template <int BLOCK_N, int MODE, int NPW, int EPI>
+__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE, EPI>::CTAS_PER_SM)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
               const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
   constexpr bool A_TMA = (MODE == MODE_CONV_TMA || MODE == MODE_CONV_TMA_AS);
   constexpr bool A_STAT = (MODE == MODE_CONV_TMA_AS);   // A tile of an m-tile stays resident while all n-tiles stream B
   constexpr int EPI_THREADS = A_TMA ? 128 + NPW * 32 : 128;
-  using C = Cfg2<BLOCK_N, MODE, SPLIT>;
+  constexpr bool SPLIT = EPI == 1;
+  constexpr bool HEAD2 = EPI == 2;
+  using C = Cfg2<BLOCK_N, MODE, EPI>;
   constexpr int STAGES = C::STAGES;
   constexpr int LAG = C::LAG;
   const bool split_out = SPLIT || p.split_out != 0;      // SPLIT == staged hi/lo tiles; narrow tiles store both halves directly
@@ -223,6 +228,46 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           }
         }
         act_chunk<CHUNK>(v, p.act, nb);
+        if constexpr (HEAD2) {
+          // ---- 1x1 heads of this branch on the fp32 hidden values of this thread's pixel (32 of the branch's 256 channels)
+          const int branch = n0 >> 8, cin0 = (n0 & 255) + ch * CHUNK;            // 256 hidden channels per branch
+          const int nout = p.h2_nch[branch];
+          const int plane = cin0 >> 5;
+          if (mvalid) {
+            const int bimg = m / HoWo, pix = m - bimg * HoWo;
+            float* dst = p.h2_part + ((static_cast<long long>(plane) * p.B + bimg) * p.h2_ntot + p.h2_ch0[branch]) * HoWo + pix;
+            const float* wb = p.h2_w + static_cast<long long>(branch) * 32 * 256 + cin0;
+            for (int o = 0; o < nout; ++o) {
+              const float* wrow = wb + o * 256;
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < CHUNK; i += 8) {
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(wrow + i));
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(wrow + i + 4));
+                acc0 += v[i] * wa.x + v[i + 1] * wa.y + v[i + 2] * wa.z + v[i + 3] * wa.w;
+                acc1 += v[i + 4] * wc.x + v[i + 5] * wc.y + v[i + 6] * wc.z + v[i + 7] * wc.w;
+              }
+              dst[static_cast<long long>(o) * HoWo] = acc0 + acc1;
+            }
+            // hidden pair rows for the edge fusion: two branches only, border pixels only
+            const int hc = p.h2_hid_col[branch];
+            if (hc >= 0 && p.h2_mask[m] != 0) {
+              __half* yp = reinterpret_cast<__half*>(p.y) + static_cast<long long>(m) * p.y_ld + hc + cin0;
+#pragma unroll
+              for (int i = 0; i < CHUNK; i += 8) {
+                __half2 o[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  o[e] = __floats2half2_rn(v[i + 2 * e], v[i + 2 * e + 1]);
+                  const float2 h = __half22float2(o[e]);
+                  l[e] = __floats2half2_rn(v[i + 2 * e] - h.x, v[i + 2 * e + 1] - h.y);
+                }
+                *reinterpret_cast<uint4*>(yp + i) = *reinterpret_cast<uint4*>(o);
+                *reinterpret_cast<uint4*>(yp + p.y_lo + i) = *reinterpret_cast<uint4*>(l);
+              }
+            }
+          }
+        } else
         if (p.out_mode == OUT_F16_NHWC) {
           if (staged) {
             if constexpr (BLOCK_N >= 64) {
@@ -724,11 +769,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, int MODE, int NPW, bool SPLIT = false>
+template <int BLOCK_N, int MODE, int NPW, int EPI = 0>
 static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tx, const IgemmParams& p,
                        int use_tma_store, cudaStream_t st) {
-  using C = Cfg2<BLOCK_N, MODE, SPLIT>;
-  auto kern = igemm2_kernel<BLOCK_N, MODE, NPW, SPLIT>;
+  using C = Cfg2<BLOCK_N, MODE, EPI>;
+  auto kern = igemm2_kernel<BLOCK_N, MODE, NPW, EPI>;
   static int attr_smem = 0;
   int smem = C::SMEM + g_tunable[MODE == MODE_DCN ? 0 : 1];
   if (smem > 227 * 1024) smem = 227 * 1024;
@@ -743,10 +788,43 @@ static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUten
   return check_cuda(launch_k(kern, dim3(grid), dim3((NPW + 6) * 32), smem, st, tw, ty, tx, p, use_tma_store), "igemm2 launch");
 }
 
+// out[b, ch, pix] = bias[ch] + sum over the eight partial planes (fixed order: deterministic), ch < ncls -> cls, else reg
+__global__ void head2_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ cls,
+                                    float* __restrict__ reg, int B, int ncls, int nreg, int HW) {
+  pdl_wait();
+  const int ntot = ncls + nreg;
+  const long long plane = static_cast<long long>(B) * ntot * HW;
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= plane) return;
+  float4 s = __ldg(reinterpret_cast<const float4*>(part + i));
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(part + q * plane + i));
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  }
+  const long long row = i / HW;                       // HW % 4 == 0 is checked by the launcher: 4 elements share (b, ch)
+  const int ch = static_cast<int>(row % ntot), b = static_cast<int>(row / ntot);
+  const int pix = static_cast<int>(i - row * HW);
+  const float bv = __ldg(bias + ch);
+  s.x += bv; s.y += bv; s.z += bv; s.w += bv;
+  float* dst = ch < ncls ? cls + (static_cast<long long>(b) * ncls + ch) * HW + pix
+                         : reg + (static_cast<long long>(b) * nreg + (ch - ncls)) * HW + pix;
+  *reinterpret_cast<float4*>(dst) = s;
+}
+int launch_head2_reduce(const float* part, const float* bias, float* cls, float* reg, int B, int ncls, int nreg, int HW,
+                        cudaStream_t st) {
+  if (HW % 4 != 0) { set_error("head2_reduce: H*W must be a multiple of 4"); return -1; }
+  const long long n4 = static_cast<long long>(B) * (ncls + nreg) * HW / 4;
+  (void)launch_k(head2_reduce_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, st, part, bias, cls, reg, B, ncls,
+                 nreg, HW);
+  return check_cuda(cudaGetLastError(), "head2_reduce");
+}
+
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st) {
   PFN_encodeTiled2 enc = encode_fn();
   if (!enc) return -1;
-  const int bn = igemm_block_n(p.Cout);
+  // HEAD2: 256-column tiles (one branch per tile) - the GEMM is bound by L2 -> smem operand traffic, see DESIGN.md
+  const int bn = (p.h2_w != nullptr && g_tunable[12] == 0) ? 256 : igemm_block_n(p.Cout);
   if (n_pad % bn != 0 || k_pad % BK != 0 || k_pad < p.nkb * BK) {
     set_error("igemm: packed weight shape [%d,%d] incompatible with block_n=%d nkb=%d", n_pad, k_pad, bn, p.nkb);
     return -1;
@@ -841,13 +919,21 @@ int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, 
     pp.nkb = 2 * p.kh * p.kw * (p.Cin / 64);
   }
   const int ntn_host = (p.Cout + bn - 1) / bn;
+  if (p.h2_w != nullptr) {                     // HEAD2 epilogue: the strict-precision predictor GEMM (see IgemmParams)
+    if (!(a_tma && (bn == 128 || bn == 256) && pp.pair && p.Cout % 256 == 0 && p.h2_part != nullptr && p.Cout / 256 <= 12)) {
+      set_error("igemm2 HEAD2: needs the pair-schedule TMA path with 128/256-column tiles and Cout a multiple of 256");
+      return -1;
+    }
+    if (bn == 256) return launch2_cfg<256, MODE_CONV_TMA, 4, 2>(tw, ty, tx, pp, 0, st);
+    return launch2_cfg<128, MODE_CONV_TMA, 4, 2>(tw, ty, tx, pp, 0, st);
+  }
   if (p.split_out && use_tma_store) {          // staged hi/lo tiles: the SPLIT instantiations (N tiles of 64 / 128 only)
-    if (mode == MODE_DCN && bn == 64) return launch2_cfg<64, MODE_DCN, 16, true>(tw, ty, tx, pp, use_tma_store, st);
-    if (mode == MODE_DCN && bn == 128) return launch2_cfg<128, MODE_DCN, 16, true>(tw, ty, tx, pp, use_tma_store, st);
-    if (a_tma && bn == 64) return launch2_cfg<64, MODE_CONV_TMA, 4, true>(tw, ty, tx, pp, use_tma_store, st);
-    if (a_tma && bn == 128) return launch2_cfg<128, MODE_CONV_TMA, 4, true>(tw, ty, tx, pp, use_tma_store, st);
-    if (bn == 64) return launch2_cfg<64, MODE_CONV, 4, true>(tw, ty, tx, pp, use_tma_store, st);
-    if (bn == 128) return launch2_cfg<128, MODE_CONV, 4, true>(tw, ty, tx, pp, use_tma_store, st);
+    if (mode == MODE_DCN && bn == 64) return launch2_cfg<64, MODE_DCN, 16, 1>(tw, ty, tx, pp, use_tma_store, st);
+    if (mode == MODE_DCN && bn == 128) return launch2_cfg<128, MODE_DCN, 16, 1>(tw, ty, tx, pp, use_tma_store, st);
+    if (a_tma && bn == 64) return launch2_cfg<64, MODE_CONV_TMA, 4, 1>(tw, ty, tx, pp, use_tma_store, st);
+    if (a_tma && bn == 128) return launch2_cfg<128, MODE_CONV_TMA, 4, 1>(tw, ty, tx, pp, use_tma_store, st);
+    if (bn == 64) return launch2_cfg<64, MODE_CONV, 4, 1>(tw, ty, tx, pp, use_tma_store, st);
+    if (bn == 128) return launch2_cfg<128, MODE_CONV, 4, 1>(tw, ty, tx, pp, use_tma_store, st);
   }
   if (mode == MODE_DCN && p.split_in) { set_error("dcn igemm: strict precision needs the staged TMA-store epilogue"); return -1; }
 #define MF_DISPATCH2(BN)                                                                          \

@@ -45,11 +45,24 @@ struct IgemmParams {
   // one third less operand traffic into shared memory than the K-concatenation (which loads A_hi and W_hi twice).
   // nkb then counts stage fills = 2 * taps * Cin / 64.
   int pair;
+  // HEAD2 epilogue (strict-precision predictor, EPI == 2 instantiation): this GEMM is the nine 3x3 head branches (N = nbranch x 256,
+  // 128-column tiles, IABN + leaky folded into scale / shift / act). Instead of storing the hidden tile, every epilogue thread
+  // contracts its 32 fp32 hidden values with the branch's 1x1 head weights (fp32, <= 32 outputs) and writes the partial dot
+  // products to plane (n_tile_in_branch * 4 + chunk) of `h2_part` [8][B][h2_ntot][Ho*Wo]; mf_head2_reduce sums the eight planes
+  // in a fixed order (+ bias) into the fp32 NCHW cls / reg maps. The hidden pair rows are stored only for the branches the edge
+  // fusion gathers (h2_hid_col >= 0) and only at the pixels flagged in h2_mask.
+  const float* h2_w;             // [nbranch][32][256] fp32, rows >= h2_nch[b] unused
+  float* h2_part;
+  int h2_ntot;                   // channels of the combined output (cls + reg = 53)
+  int h2_nch[12], h2_ch0[12], h2_hid_col[12];
+  const unsigned char* h2_mask;
 };
 
 int igemm_block_n(int cout);
 int launch_conv_wgrad_narrow(const __half* x, int x_ld, int B, int H, int W, const __half* dy, int dy_ld, int k, float* dw,
                              cudaStream_t st);
+int launch_head2_reduce(const float* part, const float* bias, float* cls, float* reg, int B, int ncls, int nreg, int HW,
+                        cudaStream_t st);
 int launch_igemm2(const IgemmParams& p, const __half* wp, int n_pad, int k_pad, int mode, cudaStream_t st);
 int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar, const __half* wp, int n_pad, int k_pad,
                      int kh, int kw, int stride, int pad, int Cout, const float* scale, const float* shift, int act,
