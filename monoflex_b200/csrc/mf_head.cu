@@ -73,7 +73,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* sc_s = reinterpret_cast<float*>(w2_smem + 2 * H_W2 + 1024);
   float* sh_s = sc_s + HBN;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int ntn = p.nbranch * 2;
   const int ntm = (p.M + HBM - 1) / HBM;
   const int HW = p.H * p.W;
@@ -99,8 +99,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   pdl_wait();
 
   if (warp == 4) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
+    // ================================================================ TMA producer (all lanes walk the loops, one issues)
+    {
       int stage = 0, bc = 0;
       uint32_t phase = 0;
       for (int mt = blockIdx.x; mt - crank < ntm; mt += gridDim.x) {   // CL: the pair runs the same trip count
@@ -111,22 +111,28 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           if ((nt & 1) == 0) {                                       // 1x1 weights of branch nt/2 -> w2 ring
             const int buf = bc & 1;
             mbar_wait(&w2_empty[buf], ((bc >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&w2_full[buf], H_W2);
-            for (int kk = 0; kk < 4; ++kk)
-              tma_load_2d(smem_u32(w2_smem + buf * H_W2 + kk * 32 * 128), &tmap_w2, &w2_full[buf], kk * 64, (nt >> 1) * 32);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&w2_full[buf], H_W2);
+              for (int kk = 0; kk < 4; ++kk)
+                tma_load_2d(smem_u32(w2_smem + buf * H_W2 + kk * 32 * 128), &tmap_w2, &w2_full[buf], kk * 64, (nt >> 1) * 32);
+            }
+            __syncwarp();
             ++bc;
           }
           int tap = 0, c0 = 0, kx = 0, ky = 0;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], H_ASTAGE + H_BSTAGE);
-            tma_load_im2col_4d(smem_u32(a_smem + stage * H_ASTAGE), &tmap_x, &full_bar[stage], c0, cw, chh, cn,
-                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
-            if (CL)
-              tma_load_2d_mc(smem_u32(b_smem + stage * H_BSTAGE + crank * (HBN / 2) * 128), &tmap_w, &full_bar[stage],
-                             kb * HBK, nt * HBN + crank * (HBN / 2), static_cast<uint16_t>(3));
-            else
-              tma_load_2d(smem_u32(b_smem + stage * H_BSTAGE), &tmap_w, &full_bar[stage], kb * HBK, nt * HBN);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], H_ASTAGE + H_BSTAGE);
+              tma_load_im2col_4d(smem_u32(a_smem + stage * H_ASTAGE), &tmap_x, &full_bar[stage], c0, cw, chh, cn,
+                                 static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+              if (CL)
+                tma_load_2d_mc(smem_u32(b_smem + stage * H_BSTAGE + crank * (HBN / 2) * 128), &tmap_w, &full_bar[stage],
+                               kb * HBK, nt * HBN + crank * (HBN / 2), static_cast<uint16_t>(3));
+              else
+                tma_load_2d(smem_u32(b_smem + stage * H_BSTAGE), &tmap_w, &full_bar[stage], kb * HBK, nt * HBN);
+            }
+            __syncwarp();
             c0 += HBK;
             if (c0 >= p.Cin) { c0 = 0; ++tap; if (++kx == 3) { kx = 0; ++ky; } }
             if (++stage == H_STAGES) { stage = 0; phase ^= 1; }
@@ -135,8 +141,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
   } else if (warp == 5) {
-    // ================================================================ MMA issuer (main GEMM + deferred stage 2)
-    if (lane == 0) {
+    // ================================================================ MMA issuer (main GEMM + deferred stage 2): every lane
+    // walks the loops and waits, one elected lane issues (see elect_one in mf_common.cuh)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(HBM, HBN);
       constexpr uint32_t idesc2 = umma_idesc_f16(HBM, 32);
       const uint64_t a_d0 = umma_desc_sw128(smem_u32(a_smem)), b_d0 = umma_desc_sw128(smem_u32(b_smem));
@@ -152,14 +159,17 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_wait(s2_full, tj & 1);
         tc_fence_after();
         const uint32_t d2 = tmem_base + H_TMEM_D2 + buf * 32;
+        if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+          for (int s = 0; s < 2; ++s)
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_f16(d2, o_d0 + ((s * H_ASTAGE) >> 4) + 2 * k4,
-                     w2_d0 + ((buf * H_W2 + (2 * h + s) * 32 * 128) >> 4) + 2 * k4, idesc2, (h | s | k4) != 0 ? 1u : 0u);
-        umma_commit(s2_done);
-        if (h == 1) { umma_commit(&d2_full[buf]); umma_commit(&w2_empty[buf]); }
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_f16(d2, o_d0 + ((s * H_ASTAGE) >> 4) + 2 * k4,
+                       w2_d0 + ((buf * H_W2 + (2 * h + s) * 32 * 128) >> 4) + 2 * k4, idesc2, (h | s | k4) != 0 ? 1u : 0u);
+          umma_commit(s2_done);
+          if (h == 1) { umma_commit(&d2_full[buf]); umma_commit(&w2_empty[buf]); }
+        }
+        __syncwarp();
       };
       for (int mt = blockIdx.x; mt - crank < ntm; mt += gridDim.x) {   // CL: the pair runs the same trip count
         for (int nt = 0; nt < ntn; ++nt, ++ti) {
@@ -172,20 +182,22 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tc_fence_after();
             const uint64_t a_off = static_cast<uint64_t>((stage * H_ASTAGE) >> 4);
             const uint64_t b_off = static_cast<uint64_t>((stage * H_BSTAGE) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k4 = 0; k4 < HBK / 16; ++k4)
-              umma_f16(d_tmem, a_d0 + a_off + 2 * k4, b_d0 + b_off + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-            if (CL) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));
-            else umma_commit(&empty_bar[stage]);
+              for (int k4 = 0; k4 < HBK / 16; ++k4)
+                umma_f16(d_tmem, a_d0 + a_off + 2 * k4, b_d0 + b_off + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+              if (CL) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));
+              else umma_commit(&empty_bar[stage]);
+              if (kb == nkb - 1) umma_commit(&acc_full[acc]);
+            }
+            __syncwarp();
             if (++stage == H_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&acc_full[acc]);
           if (ti >= 1) stage2(ti - 1);
         }
       }
       if (ti >= 1) stage2(ti - 1);
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue: warps 6-9 = group 0, warps 0-3 = group 1
     const int group = warp < 4 ? 1 : 0;

@@ -6,7 +6,7 @@
 
 namespace mf {
 
-enum { MODE_CONV = 0, MODE_DCN = 1, MODE_CONV_TMA = 2, MODE_CONV_TMA_AS = 3 };
+enum { MODE_CONV = 0, MODE_DCN = 1, MODE_CONV_TMA = 2, MODE_CONV_TMA_AS = 3, MODE_CONV_PATCH = 4 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFMASK = 3 };
 enum { OUT_F16_NHWC = 0, OUT_F32_NHWC = 1, OUT_F32_NCHW = 2 };
 

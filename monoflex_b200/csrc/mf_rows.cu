@@ -3,7 +3,8 @@
 // (G = channel-planes x column-parities), and the implicit-GEMM A operand is never materialised:
 //
 //   * per output tile (128 consecutive pixels of one output row) the TMA warp loads each needed input row segment ONCE
-//     (136 pixels x 16 B, one tiled 5-D cp.async.bulk.tensor per (row, plane, parity), zero fill outside the image);
+//     (144 pixels x 16 B, two tiled cp.async.bulk.tensor boxes of 8-byte elements per (row, plane, parity), zero fill outside
+//     the image);
 //   * the MMA warp reads the im2col matrix *through descriptors*: with the no-swizzle K-major layout a core matrix is
 //     8 rows x 16 B with rows 16 B apart, which is exactly "8 consecutive pixels" of a segment, so
 //       A[r, tap kx] = segment[(r + kx) * 16 B]      -> start address + kx*16, SBO = 128 (8 pixels)
@@ -20,8 +21,8 @@
 namespace mf {
 
 static constexpr int RBM = 128;
-static constexpr int SEG_PIX = 136;
-static constexpr int SEG_BYTES = SEG_PIX * 16;     // 2176 = 17 * 128
+static constexpr int SEG_PIX = 144;                // 128 + 2 x 4 halo, rounded so that half a segment is a multiple of 128 B
+static constexpr int SEG_BYTES = SEG_PIX * 16;     // 2304 = 18 * 128
 static constexpr int R_STAGES = 6;
 static constexpr int MAX_SEG = 12;
 static constexpr int MAX_MMA = 56;          // strict precision: 2 x 28 (image pair plane) or 3 x 9 (pair planes) products
@@ -45,14 +46,6 @@ struct RowsParams {
   int y_lo;
 };
 
-MF_DEVINL void tma_load_5d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
-          "r"(dst_smem),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
 template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 2)
 rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -73,7 +66,7 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
   uint64_t* desc_tab = w_bar + 2;                              // [2 * MAX_MMA]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler
   const int tiles_x = (p.Wo + RBM - 1) / RBM;
   const int ntiles = p.B * p.Ho * tiles_x;
   constexpr int ACC_COLS = 32;
@@ -95,10 +88,14 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (warp == 0) {
     // ================================================================ TMA: resident weights, then row segments per tile
-    if (lane == 0) {
-      mbar_arrive_expect_tx(w_bar, p.nkb * BLOCK_N * 128);
-      for (int kb = 0; kb < p.nkb; ++kb)
-        tma_load_2d(smem_u32(b_smem + kb * BLOCK_N * 128), &tmap_w, w_bar, kb * 64, 0);
+    // (all lanes walk the loop, one elected lane issues)
+    {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_bar, p.nkb * BLOCK_N * 128);
+        for (int kb = 0; kb < p.nkb; ++kb)
+          tma_load_2d(smem_u32(b_smem + kb * BLOCK_N * 128), &tmap_w, w_bar, kb * 64, 0);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -106,26 +103,32 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int oy = row % p.Ho, b = row / p.Ho;
         const int ox0 = tx * RBM;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         const uint32_t dst = smem_u32(a_smem + stage * stage_stride);
-        for (int sgi = 0; sgi < p.nseg; ++sgi)
-          tma_load_5d(dst + sgi * SEG_BYTES, &tmap_x, &full_bar[stage], 0, ox0 + p.seg_dx[sgi], p.seg_g[sgi],
-                      oy * p.stride + p.seg_dy[sgi], b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          for (int sgi = 0; sgi < p.nseg; ++sgi) {             // a segment = two boxes of 144 eight-byte elements (see host)
+            const int xe = 2 * (ox0 + p.seg_dx[sgi]), yy = oy * p.stride + p.seg_dy[sgi];
+            tma_load_4d(dst + sgi * SEG_BYTES, &tmap_x, &full_bar[stage], xe, p.seg_g[sgi], yy, b);
+            tma_load_4d(dst + sgi * SEG_BYTES + SEG_BYTES / 2, &tmap_x, &full_bar[stage], xe + SEG_PIX, p.seg_g[sgi], yy, b);
+          }
+        }
+        __syncwarp();
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
+    // ================================================================ MMA issuer (all lanes walk the loop, one issues)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(RBM, BLOCK_N);
       mbar_wait(w_bar, 0);
       tc_fence_after();
       const uint32_t a0 = smem_u32(a_smem), b0 = smem_u32(b_smem);
       // descriptor tables in smem (stage 0 addresses): the issue loop is ld.shared + 64-bit add per MMA
-      for (int i = 0; i < p.nmma; ++i) {
+      for (int i = lane; i < p.nmma; i += 32) {
         desc_tab[2 * i] = umma_desc_kmajor(a0 + p.mma_a[i], p.mma_lbo[i], 128, 0);
         desc_tab[2 * i + 1] = umma_desc_sw128(b0 + p.mma_b[i]);
       }
+      __syncwarp();
       const int nmma = p.nmma;
       int stage = 0, ti = 0;
       uint32_t phase = 0;
@@ -136,15 +139,17 @@ rows_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         const uint64_t a_off = static_cast<uint64_t>((stage * stage_stride) >> 4);
+        if (elect_one()) {
 #pragma unroll 7
-        for (int i = 0; i < nmma; ++i)
-          umma_f16(d_tmem, desc_tab[2 * i] + a_off, desc_tab[2 * i + 1], idesc, i != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&acc_full[acc]);
+          for (int i = 0; i < nmma; ++i)
+            umma_f16(d_tmem, desc_tab[2 * i] + a_off, desc_tab[2 * i + 1], idesc, i != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue (warps 2..5)
     const int quad = warp & 3;
@@ -310,13 +315,18 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
   // ---- tensor maps
   CUtensorMap tx, tw;
   {
-    cuuint64_t gdim[5] = {8, static_cast<cuuint64_t>(p.Wg_in), static_cast<cuuint64_t>(p.Gin), static_cast<cuuint64_t>(H),
+    // A plane row is contiguous (Wg pixels x 16 B). Described with its natural {8 ch, Wg, ..} dimensions the TMA unit issues
+    // one 16-byte request per pixel and a tile's 7-12 segments cost ~1000-1600 requests (the kernel was request-bound:
+    // 2.5 us per 128-pixel tile). As 8-byte elements a row is ONE dimension of 2*Wg elements; a box holds <= 256 elements,
+    // so a 144-pixel segment is two boxes of 144 elements (1152 B each, TMA needs 128-byte aligned smem destinations).
+    // Out-of-range elements are zero-filled as before.
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(p.Wg_in) * 2, static_cast<cuuint64_t>(p.Gin), static_cast<cuuint64_t>(H),
                           static_cast<cuuint64_t>(B)};
-    cuuint64_t gstr[4] = {16, static_cast<cuuint64_t>(p.Wg_in) * 16, static_cast<cuuint64_t>(p.Wg_in) * 16 * p.Gin,
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.Wg_in) * 16, static_cast<cuuint64_t>(p.Wg_in) * 16 * p.Gin,
                           static_cast<cuuint64_t>(p.Wg_in) * 16 * p.Gin * H};
-    cuuint32_t box[5] = {8, SEG_PIX, 1, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(x), gdim, gstr, box, estr,
+    cuuint32_t box[4] = {SEG_PIX, 1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<__half*>(x), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("rows_conv: cuTensorMapEncodeTiled(x) failed (%d)", static_cast<int>(r)); return -1; }

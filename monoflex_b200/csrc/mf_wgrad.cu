@@ -50,7 +50,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   uint64_t* acc_full = empty_bar + WG_STAGES;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int nitems = p.ntm * p.ntn * p.splits;
   const int HoWo = p.Ho * p.Wo, cblocks = p.Cin / AW;
 
@@ -78,8 +78,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   };
 
   if (warp == 4) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
+    // ================================================================ TMA producer (all lanes walk the loops, one issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -98,24 +98,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           const int n = p0 / HoWo, rem = p0 - n * HoWo;
           const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + NB * B_BOX);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + NB * B_BOX);
 #pragma unroll
-          for (int h = 0; h < SPT; ++h) {
-            const int ky = s_tap[h] / p.kw, kx = s_tap[h] - ky * p.kw;
-            tma_load_im2col_4d(smem_u32(a_smem + stage * A_STAGE + h * A_BOX), &tmap_x, &full_bar[stage], s_c0[h],
-                               ox * p.stride - p.pad_w, oy * p.stride - p.pad_h, n, static_cast<uint16_t>(kx),
-                               static_cast<uint16_t>(ky));
+            for (int h = 0; h < SPT; ++h) {
+              const int ky = s_tap[h] / p.kw, kx = s_tap[h] - ky * p.kw;
+              tma_load_im2col_4d(smem_u32(a_smem + stage * A_STAGE + h * A_BOX), &tmap_x, &full_bar[stage], s_c0[h],
+                                 ox * p.stride - p.pad_w, oy * p.stride - p.pad_h, n, static_cast<uint16_t>(kx),
+                                 static_cast<uint16_t>(ky));
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              tma_load_2d(smem_u32(b_smem + stage * B_STAGE + j * B_BOX), &tmap_dy, &full_bar[stage], nt * BLOCK_N + j * BW, p0);
           }
-#pragma unroll
-          for (int j = 0; j < NB; ++j)
-            tma_load_2d(smem_u32(b_smem + stage * B_STAGE + j * B_BOX), &tmap_dy, &full_bar[stage], nt * BLOCK_N + j * BW, p0);
+          __syncwarp();
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
+    // ================================================================ MMA issuer (all lanes walk the loops, one issues)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N) | (1u << 15) | (1u << 16);      // A and B MN-major
       const uint64_t a_d0 = umma_desc_kmajor(smem_u32(a_smem), A_BOX, 16 * AW, wg_layout(AW));
       const uint64_t b_d0 = umma_desc_kmajor(smem_u32(b_smem), B_BOX, 16 * BW, wg_layout(BW));
@@ -130,17 +133,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_off = static_cast<uint64_t>((stage * A_STAGE) >> 4), b_off = static_cast<uint64_t>((stage * B_STAGE) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < WG_BK / 16; ++k4)                 // 16 pixels = two 8-row groups (2 * SBO) per MMA
-            umma_f16(tmem_base, a_d0 + a_off + static_cast<uint64_t>(k4 * ((2 * 16 * AW) >> 4)),
-                     b_d0 + b_off + static_cast<uint64_t>(k4 * ((2 * 16 * BW) >> 4)), idesc, (kb > kb_lo || k4 != 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            for (int k4 = 0; k4 < WG_BK / 16; ++k4)               // 16 pixels = two 8-row groups (2 * SBO) per MMA
+              umma_f16(tmem_base, a_d0 + a_off + static_cast<uint64_t>(k4 * ((2 * 16 * AW) >> 4)),
+                       b_d0 + b_off + static_cast<uint64_t>(k4 * ((2 * 16 * BW) >> 4)), idesc, (kb > kb_lo || k4 != 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb_hi - 1) umma_commit(acc_full);
+          }
+          __syncwarp();
           if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(acc_full);
+        if (kb_hi <= kb_lo) {                                     // empty K range (host never asks for more splits than blocks)
+          if (elect_one()) umma_commit(acc_full);
+          __syncwarp();
+        }
       }
     }
-    __syncwarp();
   } else {
     // ================================================================ epilogue: TMEM -> fp32 atomics into OIHW dW
     const int row = warp * 32 + lane;                              // M index inside the tile

@@ -37,8 +37,8 @@ def pick(plan, name, pred):
 if model.precision == "strict":
     # strict precision: pair kernels (argument lists of engine.py's x2 emitters)
     sel_spec = [
-        ("head", hp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 2304),
-        ("head_1x1", hp, "mf_conv2d_nhwc_f16x2", lambda a: a[10] == 1 and a[14] == 20),
+        ("head", hp, "mf_head_conv_f16x2", lambda a: True),
+        ("head2_reduce", hp, "mf_head2_reduce", lambda a: True),
         ("dcn64", bp, "mf_dcn_nhwc_f16x2", lambda a: a[6] == 64 and a[4] == 96),
         ("dcn128", bp, "mf_dcn_nhwc_f16x2", lambda a: a[6] == 128 and a[4] == 48),
         ("offconv64", bp, "mf_conv2d_nhwc_f16x2", lambda a: a[14] == 27 and a[6] == 64 and a[4] == 96),
