@@ -79,7 +79,7 @@ MF_DEVINL void act_chunk(float (&v)[N], int act, int nb) {
 
 // EPI: 0 = plain epilogue, 1 = SPLIT (staged hi/lo output tiles), 2 = HEAD2 (1x1 head contraction in the epilogue, see IgemmParams)
 template <int BLOCK_N, int MODE, int NPW, int EPI>
-__global__ void __launch_bounds__((NPW + 6) * 32, Cfg2<BLOCK_N, MODE, EPI>::CTAS_PER_SM)
+__global__ void __launch_bounds__((NPW + (MODE == MODE_CONV_PATCH ? 7 : 6)) * 32, Cfg2<BLOCK_N, MODE, EPI>::CTAS_PER_SM)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_y,
               const __grid_constant__ CUtensorMap tmap_x, const IgemmParams p, const int use_tma_store) {
   constexpr bool PATCH = (MODE == MODE_CONV_PATCH);     // 16 x 8 pixel m-tiles, A from kx-shifted patch slots (see PATCH_SLOT)
@@ -256,17 +256,28 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             const int bimg = m / HoWo, pix = m - bimg * HoWo;
             float* dst = p.h2_part + ((static_cast<long long>(plane) * p.B + bimg) * p.h2_ntot + p.h2_ch0[branch]) * HoWo + pix;
             const float* wb = p.h2_w + static_cast<long long>(branch) * 32 * 256 + cin0;
-            for (int o = 0; o < nout; ++o) {
-              const float* wrow = wb + o * 256;
-              float acc0 = 0.f, acc1 = 0.f;
+            // two outputs per pass (the second row of an odd tail re-reads the first and is not stored): 16 independent
+            // 16-byte weight loads in flight and four independent FMA chains per thread - the epilogue, not the tensor pipe,
+            // is what the accumulator hand-over waits on once the MMA issue is tight
+            for (int o = 0; o < nout; o += 2) {
+              const float* wr0 = wb + o * 256;
+              const float* wr1 = (o + 1 < nout) ? wr0 + 256 : wr0;
+              float4 wa[CHUNK / 4], wc[CHUNK / 4];
 #pragma unroll
-              for (int i = 0; i < CHUNK; i += 8) {
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(wrow + i));
-                const float4 wc = __ldg(reinterpret_cast<const float4*>(wrow + i + 4));
-                acc0 += v[i] * wa.x + v[i + 1] * wa.y + v[i + 2] * wa.z + v[i + 3] * wa.w;
-                acc1 += v[i + 4] * wc.x + v[i + 5] * wc.y + v[i + 6] * wc.z + v[i + 7] * wc.w;
+              for (int i = 0; i < CHUNK / 4; ++i) {
+                wa[i] = __ldg(reinterpret_cast<const float4*>(wr0) + i);
+                wc[i] = __ldg(reinterpret_cast<const float4*>(wr1) + i);
               }
-              dst[static_cast<long long>(o) * HoWo] = acc0 + acc1;
+              float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < CHUNK / 4; i += 2) {
+                a0 += v[4 * i] * wa[i].x + v[4 * i + 1] * wa[i].y + v[4 * i + 2] * wa[i].z + v[4 * i + 3] * wa[i].w;
+                a1 += v[4 * i + 4] * wa[i + 1].x + v[4 * i + 5] * wa[i + 1].y + v[4 * i + 6] * wa[i + 1].z + v[4 * i + 7] * wa[i + 1].w;
+                c0 += v[4 * i] * wc[i].x + v[4 * i + 1] * wc[i].y + v[4 * i + 2] * wc[i].z + v[4 * i + 3] * wc[i].w;
+                c1 += v[4 * i + 4] * wc[i + 1].x + v[4 * i + 5] * wc[i + 1].y + v[4 * i + 6] * wc[i + 1].z + v[4 * i + 7] * wc[i + 1].w;
+              }
+              dst[static_cast<long long>(o) * HoWo] = a0 + a1;
+              if (o + 1 < nout) dst[static_cast<long long>(o + 1) * HoWo] = c0 + c1;
             }
             // hidden pair rows for the edge fusion: two branches only, border pixels only
             const int hc = p.h2_hid_col[branch];
@@ -600,9 +611,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       }
     }
   } else if (warp == NPW && PATCH) {
-    // ================================================================ patch mode: lane 0 streams weight stages, lane 1 A slots
-    // (two independent in-order producers: the A ring runs as far ahead as its slots allow, whatever the weight ring does)
-    if (lane == 0) {
+    // ================================================================ patch mode: this warp streams the weight stages ...
+    {
       int stage = 0;
       uint32_t phase = 0;
       MF_TILE_LOOP {
@@ -613,13 +623,20 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               const int g = (ky * 3 + kx) * p_nchunk + c;          // (tap, chunk) group of the packed weight K axis
               for (int h = 0; h < p_nh; ++h) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], B_STAGE);
-                tma_load_2d(smem_u32(b_smem + stage * B_STAGE), &tmap_w, &full_bar[stage], (p.split_in ? 3 * g + 2 * h : g) * BK, n0);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&full_bar[stage], B_STAGE);
+                  tma_load_2d(smem_u32(b_smem + stage * B_STAGE), &tmap_w, &full_bar[stage], (p.split_in ? 3 * g + 2 * h : g) * BK, n0);
+                }
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
             }
       }
-    } else if (lane == 1) {
+    }
+  } else if (PATCH && warp == NPW + 6) {
+    // ================================================================ ... and an extra warp the A slots: two independent
+    // in-order producers (in one warp the two wait loops would serialise: a try_wait suspends the whole warp)
+    {
       int fa = 0;                                                  // running slot-fill counter: slot fa % NSLOT
       for (int outer = blockIdx.x; outer < n_outer; outer += gridDim.x) {
         const int tile_b = outer / (tiles_x * tiles_y);
@@ -632,14 +649,16 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
               for (int h = 0; h < p_nh; ++h) {
                 const int s = fa % NSL;
                 mbar_wait(&a_empty[s], (((fa / NSL) & 1) ^ 1));
-                mbar_arrive_expect_tx(&a_full[s], PATCH_SLOT);
-                tma_load_4d(smem_u32(a_smem + s * PATCH_SLOT), &tmap_x, &a_full[s], c * 64 + (h ? p.x_lo : 0), x0 + kx - 1, y0 - 1,
-                            tile_b);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&a_full[s], PATCH_SLOT);
+                  tma_load_4d(smem_u32(a_smem + s * PATCH_SLOT), &tmap_x, &a_full[s], c * 64 + (h ? p.x_lo : 0), x0 + kx - 1, y0 - 1,
+                              tile_b);
+                }
+                __syncwarp();
                 ++fa;
               }
       }
     }
-    __syncwarp();
   } else if (warp == NPW) {
     // ================================================================ weight tiles by TMA (all lanes walk, one issues)
     {
@@ -920,7 +939,9 @@ static int launch2_cfg(const CUtensorMap& tw, const CUtensorMap& ty, const CUten
   int grid = num_sms() * C::CTAS_PER_SM;
   if (grid > ntn * ntm) grid = ntn * ntm;
   if (MODE == MODE_CONV_PATCH && grid > ntm) grid = ntm;       // m-tiles are strided over CTAs, n-tiles run inside
-  return check_cuda(launch_k(kern, dim3(grid), dim3((NPW + 6) * 32), smem, st, tw, ty, tx, p, use_tma_store), "igemm2 launch");
+  return check_cuda(launch_k(kern, dim3(grid), dim3((NPW + (MODE == MODE_CONV_PATCH ? 7 : 6)) * 32), smem, st, tw, ty, tx, p,
+                             use_tma_store),
+                    "igemm2 launch");
 }
 
 // out[b, ch, pix] = bias[ch] + sum over the eight partial planes (fixed order: deterministic), ch < ncls -> cls, else reg

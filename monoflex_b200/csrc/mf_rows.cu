@@ -24,7 +24,7 @@ static constexpr int RBM = 128;
 static constexpr int SEG_PIX = 144;                // 128 + 2 x 4 halo, rounded so that half a segment is a multiple of 128 B
 static constexpr int SEG_BYTES = SEG_PIX * 16;     // 2304 = 18 * 128
 static constexpr int R_STAGES = 6;
-static constexpr int MAX_SEG = 12;
+static constexpr int MAX_SEG = 24;          // strict stride-2 layer: 3 rows x 4 planes (hi0 hi1 lo0 lo1) x 2 column parities
 static constexpr int MAX_MMA = 56;          // strict precision: 2 x 28 (image pair plane) or 3 x 9 (pair planes) products
 
 struct RowsParams {
@@ -251,7 +251,7 @@ int launch_rows_conv(const __half* x, int B, int H, int W, int Cin, int in_npar,
   const int P = Cin / 8;
   const int nsets = in_mode == 1 ? 2 : (in_mode == 2 ? 3 : 1);
   const int Ptot = in_mode == 2 ? 2 * P : P;             // planes in memory (hi planes, then lo planes)
-  if (in_mode < 0 || in_mode > 2 || (in_mode == 1 && Cin != 8) || (in_mode == 2 && (Cin != 16 || stride != 1)) ||
+  if (in_mode < 0 || in_mode > 2 || (in_mode == 1 && Cin != 8) || (in_mode == 2 && Cin != 16) ||
       (split_out && !out_planar && y_lo % 8 != 0)) {
     set_error("rows_conv: unsupported strict-precision configuration (in_mode %d, Cin %d, stride %d)", in_mode, Cin, stride);
     return -1;

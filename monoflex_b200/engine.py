@@ -414,8 +414,8 @@ class Plan(object):
             wa[:, 0:3, :, :kw], wa[:, 3:6, :, :kw], wb[:, 0:3, :, :kw] = w_hi, w_hi, w_lo
             wv, cin, in_mode, in_npar = torch.cat([wa, wb], 2), 8, 1, 1
         else:
-            assert x.C == 16 and x.split and x.npar == 1 and stride == 1
-            wv, cin, in_mode, in_npar = torch.cat([w_hi, w_hi, w_lo], 2), 16, 2, 1
+            assert x.C == 16 and x.split and ((x.npar == 1 and stride == 1) or (x.npar == 2 and stride == 2))
+            wv, cin, in_mode, in_npar = torch.cat([w_hi, w_hi, w_lo], 2), 16, 2, x.npar
         wp, n_pad, k_pad = self.pack_weight(wv.contiguous(), cin_pad=cin)
         scale, shift = self.affine(cout, n_pad, bn)
         Ho, Wo = (x.H + 2 * pad - kh) // stride + 1, (x.W + 2 * pad - kw) // stride + 1

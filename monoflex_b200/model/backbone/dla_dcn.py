@@ -133,11 +133,12 @@ class DLA(nn.Module):
         y = []
         if P.strict and rows_ok:
             # strict precision on the row-segment kernel: x8 is the image pair plane [hi3 | lo3 | 0 0] (mf_pack_image_pair8);
-            # 7x7 and level0 run as extra MMAs over the same resident row segments, level0 hands NHWC pair rows to level1
+            # the split products of 7x7, level0 and the stride-2 level1 run as extra MMAs over the same resident row segments;
+            # level0 writes column-parity pair planes for level1, level1 hands NHWC pair rows to level2
             x8.npar = 1
             a0 = P.conv_rows_strict(x8, self.base_layer[0].weight, 1, 3, self.base_layer[1], out_planar=True, image=True)
-            a1 = P.conv_rows_strict(a0, self.level0[0].weight, 1, 1, self.level0[1], out_planar=False)
-            x = P.conv(a1, self.level1[0].weight, self.level1[0].stride[0], 1, self.level1[1])
+            a1 = P.conv_rows_strict(a0, self.level0[0].weight, 1, 1, self.level0[1], out_planar=True, out_npar=2)
+            x = P.conv_rows_strict(a1, self.level1[0].weight, 2, 1, self.level1[1], out_planar=False)
             y += [a1, x]
         elif P.strict:
             # generic fallback: x8 is the 16-channel pair-packed image [hi3 | lo3 | hi3 | 0 x 7] (mf_pack_image_split), so the

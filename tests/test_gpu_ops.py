@@ -180,7 +180,8 @@ def test_strict_stem_and_elementwise():
 @pytest.mark.parametrize("shape", [(2, 10, 144), (1, 7, 256), (1, 5, 40)])
 def test_strict_stem_rows_chain(shape):
     """strict stem on the row-segment kernel (mf_conv2d_rows_f16x2): image pair plane -> 7x7 (two tap sets over the same
-    resident rows) -> planar pair planes -> 3x3 (three tap sets) -> NHWC pair rows -> 3x3 stride 2 (gather GEMM on pairs)."""
+    resident rows) -> planar pair planes -> 3x3 (three tap sets) -> NHWC pair rows -> 3x3 stride 2 (gather GEMM on pairs), and the product
+    path level0 -> column-parity pair planes -> 3x3 stride 2 on the row-segment kernel (24 row segments per tile)."""
     from monoflex_b200._lib import call, stream
     B, H, W = shape
     gen = np.random.Generator(np.random.PCG64(17))
@@ -195,12 +196,18 @@ def test_strict_stem_rows_chain(shape):
     a0 = P.conv_rows_strict(x8, w0.cuda(), 1, 3, bn0, out_planar=True, image=True)
     a1 = P.conv_rows_strict(a0, w1.cuda(), 1, 1, bn1, out_planar=False)
     a2 = P.conv(a1, w2.cuda(), 2, 1, bn2)
+    # the product path: level0 writes column-parity pair planes, the stride-2 layer stays on the row-segment kernel
+    b1 = P.conv_rows_strict(a0, w1.cuda(), 1, 1, bn1, out_planar=True, out_npar=2)
+    b2 = P.conv_rows_strict(b1, w2.cuda(), 2, 1, bn2, out_planar=False)
     P.finalize()
     xc = x.cuda()
     call("mf_pack_image_pair8", xc.data_ptr(), x8.ptr(), B, 3, H, W, stream())
     P.run()
     torch.cuda.synchronize()
     g0, g1, g2 = (t.nchw_view().float().cpu() for t in (a0, a1, a2))
+    h1, h2 = (t.nchw_view().float().cpu() for t in (b1, b2))
+    assert torch.equal(h1, g1)            # same MMAs, same epilogue arithmetic: only the output layout differs
+    assert rel_err(h2, g2) < STRICT_TOL
     r0 = F.relu(bn0.cpu_apply(F.conv2d(x.double(), w0.double(), None, 1, 3).float()))
     assert rel_err(g0, r0) < STRICT_TOL
     r1 = F.relu(bn1.cpu_apply(F.conv2d(g0.double(), w1.double(), None, 1, 1).float()))
