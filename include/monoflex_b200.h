@@ -49,6 +49,12 @@ int mf_conv_block_n(int cout);
 int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                         void* out_f16, void* stream);
 
+/* Packed weights of the stride-1 DATA-GRADIENT convolution of a layer (torch autograd's conv backward w.r.t. the input,
+ * what `losses.backward()` of engine/trainer.py:112 runs through cuDNN), straight from the layer's OIHW fp32 parameter:
+ * dX = conv(dY, W^T rotated by 180 degrees, padding k-1-p); out[ci][tap' * cout_pad + co] = w[co][ci][taps-1-tap']. */
+int mf_pack_conv_weight_dgrad(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cout_pad, int n_pad, int k_pad,
+                              void* out_f16, void* stream);
+
 /* mf_pack_conv_weight for MANY tensors in one launch (training plans re-pack every weight from its live fp32 parameter at the
  * start of each step). descs_dev: DEVICE array of n descriptors of 5 int64 each: OIHW fp32 source pointer, fp16 destination
  * pointer, Cout | Cin << 32, (kh*kw) | cin_pad << 32, n_pad | k_pad << 32. */

@@ -17,6 +17,7 @@ SIGNATURES = {
     "mf_conv_block_n": [_I],
     "mf_set_tunable": [_I, _I],
     "mf_pack_conv_weight": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mf_pack_conv_weight_dgrad": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "mf_pack_conv_weights_batched": [_P, _I, _P],
     "mf_conv2d_nhwc_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _P],
     "mf_pack_conv_weight_split": [_P, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -46,6 +46,28 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, i
   return check_cuda(cudaGetLastError(), "pack_conv_weight");
 }
 
+// data-gradient weights straight from the live OIHW parameter: the stride-1 dX conv is the forward kernel on dY with the taps
+// rotated by 180 degrees and in / out channels transposed - out[n = ci][k = tap' * cout_pad + co] = w[co][ci][taps - 1 - tap']
+// (one launch instead of flip + transpose + contiguous + zero-pad cat + pack)
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int cout_pad, int n_pad,
+                                              int k_pad, __half* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n_pad) * k_pad) return;
+  const int k = static_cast<int>(i % k_pad), n = static_cast<int>(i / k_pad);
+  const int tap = k / cout_pad, co = k - tap * cout_pad;
+  float v = 0.f;
+  if (n < Cin && tap < taps && co < Cout) v = w[(static_cast<long long>(co) * Cin + n) * taps + (taps - 1 - tap)];
+  out[i] = __float2half_rn(v);
+}
+int launch_pack_conv_weight_dgrad(const float* w, int Cout, int Cin, int kh, int kw, int cout_pad, int n_pad, int k_pad,
+                                  __half* out, cudaStream_t st) {
+  if (cout_pad < Cout || k_pad < kh * kw * cout_pad || n_pad < Cin) { set_error("pack_conv_weight_dgrad: bad padding"); return -1; }
+  const long long n = static_cast<long long>(n_pad) * k_pad;
+  pack_conv_weight_dgrad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(w, Cout, Cin, kh * kw, cout_pad, n_pad,
+                                                                                       k_pad, out);
+  return check_cuda(cudaGetLastError(), "pack_conv_weight_dgrad");
+}
+
 // batched form for training plans: all weights of a plan are re-packed from their live fp32 parameters at the start of every
 // run - one launch over a device table of descriptors instead of ~190 small ones. desc (5 x int64): w ptr, out ptr,
 // Cout | Cin << 32, taps | cin_pad << 32, n_pad | k_pad << 32.
@@ -117,6 +139,11 @@ int mf_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int kh, int kw, 
                                  MF_STREAM(stream));
 }
 
+int mf_pack_conv_weight_dgrad(const float* w_oihw, int Cout, int Cin, int kh, int kw, int cout_pad, int n_pad, int k_pad,
+                              void* out_f16, void* stream) {
+  return launch_pack_conv_weight_dgrad(w_oihw, Cout, Cin, kh, kw, cout_pad, n_pad, k_pad, static_cast<__half*>(out_f16),
+                                       MF_STREAM(stream));
+}
 int mf_pack_conv_weights_batched(const void* descs_dev, int n, void* stream) {
   return launch_pack_conv_weight_batched(static_cast<const long long*>(descs_dev), n, MF_STREAM(stream));
 }

@@ -75,6 +75,8 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
                   float* s1_score, int* s1_idx, float* scores, long long* inds, float* clses, float* ys, float* xs,
                   float* pois, float* result, int* count, cudaStream_t st);
 int launch_nms_hm(const float* hm, float* out, int planes, int H, int W, cudaStream_t st);
+int launch_pack_conv_weight_dgrad(const float* w, int Cout, int Cin, int kh, int kw, int cout_pad, int n_pad, int k_pad,
+                                  __half* out, cudaStream_t st);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, int cin_pad, int n_pad, int k_pad,
                             __half* out, cudaStream_t st);
 // SyncBatchNorm halves (mf_bn_train.cu)

@@ -80,6 +80,19 @@ class Act(object):
         return self.buf.view(self.B, self.H, self.W, -1)[..., self.ch_off:self.ch_off + self.C].permute(0, 3, 1, 2)
 
 
+_CONST_VECS = {}
+
+
+def _const_vec(value, n, device):
+    """read-only fp32 vector of `n` copies of `value` (never written by any kernel: scale / shift of identity epilogues)"""
+    key = (float(value), str(device))
+    v = _CONST_VECS.get(key)
+    if v is None or v.numel() < n:
+        v = torch.full((max(n, 4096),), float(value), dtype=torch.float32, device=device)
+        _CONST_VECS[key] = v
+    return v[:n]
+
+
 class Plan(object):
     def __init__(self, device, train=False, strict=False):
         """strict=True: strict-precision inference plan (hi/lo fp16 pairs, csrc/mf_split.cu + the split paths of
@@ -242,6 +255,10 @@ class Plan(object):
 
     def affine(self, cout, n_pad, bn=None, conv_bias=None, abs_weight=False):
         """Fold eval-mode BatchNorm (dla_dcn.py:76 etc.) / InPlaceABN (|w|+eps) and the conv bias into (scale, shift)."""
+        if bn is None and conv_bias is None:
+            # identity epilogue (raw train-mode convs, every data-gradient conv of the backward tape): shared read-only
+            # constants instead of two fill kernels per plan - a captured training step replayed ~265 of them
+            return _const_vec(1.0, n_pad, self.device), _const_vec(0.0, n_pad, self.device)
         scale = torch.ones(n_pad, dtype=torch.float32, device=self.device)
         shift = torch.zeros(n_pad, dtype=torch.float32, device=self.device)
         if self.train:
@@ -342,6 +359,27 @@ class Plan(object):
             scale.data_ptr(), shift.data_ptr(), residual.ptr() if residual is not None else None,
             residual.ld if residual is not None else 0, act, OUT_F16_NHWC, y.ptr(), y.ld))
         return y
+
+    def conv_dgrad(self, dy, weight, pad, out):
+        """out += dL/dx of the stride-1 convolution y = conv(x, weight, padding=pad) given dy = dL/dy rows (its channel count
+        may be the zero-padded Cout): the forward kernel on dY with the 180-degree rotated, in/out-transposed taps, packed
+        straight from the live OIHW parameter by ONE kernel (mf_pack_conv_weight_dgrad)."""
+        cout, cin, kh, kw = weight.shape
+        assert kh == kw and kh - 1 - pad >= 0 and dy.C >= cout and (out.H, out.W) == (dy.H + kh - 1 - 2 * pad, dy.W + kw - 1 - 2 * pad)
+        w = weight.detach()
+        assert w.dtype == torch.float32 and w.is_contiguous()
+        bn_ = _lib.load().mf_conv_block_n(cin)
+        n_pad = (cin + bn_ - 1) // bn_ * bn_
+        k_pad = (kh * kw * dy.C + 63) // 64 * 64
+        wp = torch.empty(n_pad, k_pad, dtype=torch.half, device=self.device)
+        _lib.call("mf_pack_conv_weight_dgrad", w.data_ptr(), cout, cin, kh, kw, dy.C, n_pad, k_pad, wp.data_ptr(), _lib.stream())
+        self.keep.extend([w, wp])
+        scale, shift = self.affine(cin, n_pad)
+        cpad, p2 = dy.C, kh - 1 - pad
+        self.add("mf_conv2d_nhwc_f16", lambda: (
+            dy.ptr(), dy.ld, dy.B, dy.H, dy.W, cpad, wp.data_ptr(), n_pad, k_pad, kh, kw, 1, p2, cin,
+            scale.data_ptr(), shift.data_ptr(), out.ptr(), out.ld, ACT_NONE, OUT_F16_NHWC, out.ptr(), out.ld))
+        return out
 
     def conv_to_f32(self, x, weight, bias, out_tensor, out_mode, act, y_ld, stride=1, pad=0, bn=None):
         """conv whose result leaves the NHWC fp16 world: fp32 NHWC rows (offset/mask) or fp32 NCHW maps (heads)."""

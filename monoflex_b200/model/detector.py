@@ -125,7 +125,10 @@ class KeypointDetector(nn.Module):
                     p.grad = (g * inv).view_as(p)
                 else:
                     acc_dst.append(p.grad)
-                    acc_src.append(g.view_as(p))
+                    g = g.view_as(p)
+                    # the multi-tensor kernel needs dense operands; ONE strided gradient would send the whole list down the
+                    # per-tensor slow path (285 tiny add kernels per step in the ncu launch list)
+                    acc_src.append(g if g.is_contiguous() and g.dtype == p.grad.dtype else g.contiguous().to(p.grad.dtype))
         if acc_dst:                          # one multi-tensor kernel instead of ~280 tiny adds (p.grad += g / loss_scale)
             torch._foreach_add_(acc_dst, acc_src, alpha=inv)
         self.last_grad_names = used          # parameters outside the forward graph (the reference leaves their .grad None)

@@ -149,10 +149,28 @@ class DeferredLog(object):
 
     def __init__(self, out):
         self.out = out
+        self._host = None
+        self._event = None
+
+    def snapshot(self):
+        """Enqueue this evaluation's D2H read now (pinned, asynchronous) and return a log whose resolve() only waits for that
+        copy: a captured training step re-uses one device buffer, so a log that is read one step late (the host prepares
+        batch i+1 while step i runs) has to be copied out before the next replay overwrites it."""
+        snap = DeferredLog(self.out)
+        dev = torch.cat([self.out[:11], self.out[16:16 + len(LOG_KEYS)]])
+        snap._host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        snap._host.copy_(dev, non_blocking=True)
+        snap._event = torch.cuda.Event()
+        snap._event.record()
+        return snap
 
     def resolve(self):
         out = self.out
-        host = torch.cat([out[:11], out[16:16 + len(LOG_KEYS)]]).cpu()                    # the step's single D2H read
+        if self._host is not None:
+            self._event.synchronize()
+            host = self._host
+        else:
+            host = torch.cat([out[:11], out[16:16 + len(LOG_KEYS)]]).cpu()                # the step's single D2H read
         log_loss_dict = {k: float(host[11 + i]) for i, k in enumerate(LOG_KEYS)}
         for i, k in enumerate(REF_LOSS_NAMES):                                            # detector_loss.py:478-480
             if k not in log_loss_dict:

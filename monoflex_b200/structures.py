@@ -37,7 +37,17 @@ class ParamsList(object):
     def to(self, device):
         out = ParamsList(self.size, self.is_train)
         for k, v in self.extra_fields.items():
-            out.extra_fields[k] = v.to(device) if hasattr(v, "to") else v
+            if torch.is_tensor(v):     # fields in pinned host memory (a pin_memory data loader) go up without blocking the host
+                out.extra_fields[k] = v.to(device, non_blocking=v.device.type == "cpu" and v.is_pinned())
+            else:
+                out.extra_fields[k] = v.to(device) if hasattr(v, "to") else v
+        return out
+
+    def pin_memory(self):
+        """the same fields in page-locked host memory (what DataLoader(pin_memory=True) does to a batch)"""
+        out = ParamsList(self.size, self.is_train)
+        for k, v in self.extra_fields.items():
+            out.extra_fields[k] = v.pin_memory() if torch.is_tensor(v) and v.device.type == "cpu" else v
         return out
 
     def __len__(self):

@@ -98,6 +98,15 @@ def _conv_backward(G, x, weight, bias, stride, pad, d_raw, B, Ho, Wo, put, need_
     if not need_dx:
         return
     w = weight.detach().float()
+    if stride == 1 and w.is_contiguous() and kh == kw:
+        P = engine.Plan(str(dev))
+        dya = P.act(B, Ho, Wo, cout_p)
+        dya.buf = d_raw
+        gx = G.bound(P, x)
+        P.conv_dgrad(dya, w, pad, gx)                                # grad(x) += dgrad, in place (rotated taps packed in one kernel)
+        P.finalize()
+        P.run()
+        return
     if cout_p != cout:
         w = torch.cat([w, torch.zeros(cout_p - cout, cin, kh, kw, device=dev)], 0)
     if stride == 1:

@@ -133,4 +133,4 @@ class Trainer(object):
             self._exchange_and_update()
         self.scheduler.step()
         self.iteration += 1
-        return g["loss_dict"], (g["log"].resolve() if sync_log else g["log"])
+        return g["loss_dict"], (g["log"].resolve() if sync_log else g["log"].snapshot())

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python bench.py --train --steps 10 --warmup 3 > gpurun_out/r2ab_train.json 2> gpurun_out/r2ab_train.err
