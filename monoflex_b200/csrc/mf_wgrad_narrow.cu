@@ -45,26 +45,33 @@ wgrad_narrow_kernel(const __half* __restrict__ x, int x_ld, const __half* __rest
   for (int kx = 0; kx < K; ++kx) wmma::fill_fragment(acc[kx], 0.f);
 
   auto stage = [&](const long long unit, const int buf) {
-    // every thread copies 16-byte chunks: X tiles (K rows x TW pixels x 2 chunks) and dY blocks (16 pixels x 2 chunks) of G blocks
+    // every thread copies 16-byte chunks: X tiles (K rows x TW pixels x 2 chunks) and dY blocks (16 pixels x 2 chunks) of G blocks.
+    // The block -> (image row, x0) decode is done once per block in 32-bit arithmetic, not per chunk (the 64-bit divisions of
+    // the first version were the kernel: ~7 k warp instructions per 16-pixel block)
     constexpr int XCH = K * C::TW * 2, YCH = 16 * 2;
-    for (int i = threadIdx.x; i < C::G * (XCH + YCH); i += blockDim.x) {
-      const int g = i / (XCH + YCH), r = i - g * (XCH + YCH);
+#pragma unroll
+    for (int g = 0; g < C::G; ++g) {
       const long long blk = unit * C::G + g;
       const bool live = blk < nblocks;
-      const long long row = live ? blk / bw : 0;           // (b, y)
-      const int x0 = live ? static_cast<int>(blk - row * bw) * 16 : 0;
-      const int y = static_cast<int>(row % H);
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < XCH) {
-        const int half_id = r & 1, px = (r >> 1) % C::TW, ry = (r >> 1) / C::TW;
-        const int yy = y + ry - PAD, xx = x0 + px - PAD;
-        if (live && yy >= 0 && yy < H && xx >= 0 && xx < W)
-          v = __ldg(reinterpret_cast<const uint4*>(x + ((row - y + yy) * W + xx) * x_ld + half_id * 8));
-        *reinterpret_cast<uint4*>(&xs[buf][g][(ry * C::TW + px) * 16 + half_id * 8]) = v;
-      } else {
-        const int q = r - XCH, half_id = q & 1, px = q >> 1;
-        if (live && x0 + px < W) v = __ldg(reinterpret_cast<const uint4*>(dy + (row * W + x0 + px) * dy_ld + half_id * 8));
-        *reinterpret_cast<uint4*>(&ys[buf][g][px * 16 + half_id * 8]) = v;
+      const int blk32 = live ? static_cast<int>(blk) : 0;  // launcher guarantees B*H*ceil(W/16) < 2^31
+      const int row = blk32 / bw;                          // (b, y)
+      const int x0 = (blk32 - row * bw) * 16;
+      const int y = row % H;
+      const long long rowbase = static_cast<long long>(row - y) * W;     // first pixel of the image
+      for (int r = threadIdx.x; r < XCH + YCH; r += blockDim.x) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < XCH) {
+          const int half_id = r & 1, pr = r >> 1, ry = pr / C::TW, px = pr - ry * C::TW;
+          const int yy = y + ry - PAD, xx = x0 + px - PAD;
+          if (live && yy >= 0 && yy < H && xx >= 0 && xx < W)
+            v = __ldg(reinterpret_cast<const uint4*>(x + (rowbase + static_cast<long long>(yy) * W + xx) * x_ld + half_id * 8));
+          *reinterpret_cast<uint4*>(&xs[buf][g][(ry * C::TW + px) * 16 + half_id * 8]) = v;
+        } else {
+          const int q = r - XCH, half_id = q & 1, px = q >> 1;
+          if (live && x0 + px < W)
+            v = __ldg(reinterpret_cast<const uint4*>(dy + (static_cast<long long>(row) * W + x0 + px) * dy_ld + half_id * 8));
+          *reinterpret_cast<uint4*>(&ys[buf][g][px * 16 + half_id * 8]) = v;
+        }
       }
     }
   };
@@ -109,6 +116,7 @@ int launch_conv_wgrad_narrow(const __half* x, int x_ld, int B, int H, int W, con
     set_error("conv wgrad (narrow): k in {3, 7}, 16-byte aligned rows");
     return -1;
   }
+  if (static_cast<long long>(B) * H * ((W + 15) / 16) >= (1ll << 31)) { set_error("conv wgrad (narrow): too many pixel blocks"); return -1; }
   if (check_cuda(cudaMemsetAsync(dw, 0, sizeof(float) * 16 * 16 * k * k, st), "conv wgrad narrow memset")) return -1;
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
