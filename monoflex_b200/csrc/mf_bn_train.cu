@@ -272,10 +272,15 @@ static int bn_grid(long long M, int C, long long& rows_per_cta, int& threads, si
   if (CV > 256) return -1;
   const int RL = threads / CV;
   smem = static_cast<size_t>(RL) * 2 * C * sizeof(float);
-  long long ncta = (M + 1023) / 1024;                       // >= ~1024 rows per CTA keeps the fp32 partials short
+  // Enough CTAs to keep every SM's memory pipe full: up to 8 per SM, each owning a whole number of 4 x RL row groups (the
+  // kernel keeps 4 rows per thread in flight). The first version gave a CTA >= 1024 rows: 240 CTAs for the 245760-pixel maps
+  // (1.6 per SM, ~26 KB in flight per SM) and 60 for level 3 - the statistics passes ran at ~1 TB/s.
+  const long long group = 4ll * RL;
+  long long ncta = (M + group - 1) / group;
   if (ncta > 148 * 8) ncta = 148 * 8;
   if (ncta < 1) ncta = 1;
   rows_per_cta = (M + ncta - 1) / ncta;
+  rows_per_cta = (rows_per_cta + group - 1) / group * group;
   return static_cast<int>((M + rows_per_cta - 1) / rows_per_cta);
 }
 size_t bn_train_workspace_floats(long long M, int C) {
