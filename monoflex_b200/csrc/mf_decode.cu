@@ -18,15 +18,6 @@ namespace mf {
 static constexpr int S1_THREADS = 1024;
 static constexpr int S1_CAND = 2048;                   // candidate-list capacity of the rank-by-counting fast path (16 KB)
 
-MF_DEVINL float heat_value(const float* __restrict__ hm, int H, int W, int y, int x, int apply_sigmoid) {
-  float v = __ldg(hm + y * W + x);
-  if (apply_sigmoid) {
-    v = 1.f / (1.f + expf(-v));
-    v = fminf(fmaxf(v, 1e-4f), 1.f - 1e-4f);
-  }
-  return v;
-}
-
 // hm: [B, C, H, W] fp32 (already sigmoid-ed when apply_sigmoid == 0). out_*: [B, C, K]
 __global__ void __launch_bounds__(S1_THREADS)
 nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, int apply_sigmoid, int slabs,
@@ -59,6 +50,19 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
   extern __shared__ unsigned int vbits_sm[];      // [S1_ITEMS][S1_THREADS] score bits (dynamic smem, <= 128 KB)
   unsigned int* vbits = vbits_sm + threadIdx.x;   // item `it` of this thread lives at vbits[it * S1_THREADS]
   const int n_items = (hi - lo + S1_THREADS - 1) / S1_THREADS;
+  // The slab and its one-row halo are staged in shared memory first: coalesced, independent loads (6 per thread) instead of
+  // 9 dependent neighbour loads per pixel from L2 (45 per thread, the bulk of this kernel's 26 us), same arithmetic per value.
+  float* tile = reinterpret_cast<float*>(vbits_sm + static_cast<size_t>((chunk + S1_THREADS - 1) / S1_THREADS) * S1_THREADS);
+  const int t_lo = max(0, lo - W - 1), t_hi = min(HW, hi + W + 1);
+  for (int i = t_lo + static_cast<int>(threadIdx.x); i < t_hi; i += S1_THREADS) {
+    float v = __ldg(hm + i);
+    if (apply_sigmoid) {
+      v = 1.f / (1.f + expf(-v));
+      v = fminf(fmaxf(v, 1e-4f), 1.f - 1e-4f);
+    }
+    tile[i - t_lo] = v;
+  }
+  __syncthreads();
 #define MF_KEY(it) (lo + (it) * S1_THREADS + static_cast<int>(threadIdx.x) < hi                                              \
                         ? ((static_cast<unsigned long long>(vbits[(it) * S1_THREADS]) << 15) |                                         \
                            static_cast<unsigned long long>(32767 - (lo + (it) * S1_THREADS + static_cast<int>(threadIdx.x)))) + 1ull \
@@ -68,15 +72,17 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
     unsigned int key = 0u;
     if (idx < hi) {
       const int y = idx / W, x = idx - y * W;
-      const float v = heat_value(hm, H, W, y, x, apply_sigmoid);
+      const float v = tile[idx - t_lo];
       float mx = v;                                   // max_pool2d 3x3 s1 p1 (-inf padding): nms_hm utils.py:45-58
+#pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
         const int yy = y + dy;
         if (yy < 0 || yy >= H) continue;
+#pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
           const int xx = x + dx;
           if (xx < 0 || xx >= W || (dx == 0 && dy == 0)) continue;
-          mx = fmaxf(mx, heat_value(hm, H, W, yy, xx, apply_sigmoid));
+          mx = fmaxf(mx, tile[yy * W + xx - t_lo]);
         }
       }
       const float kept = (mx == v) ? v : 0.f;         // heat * (hmax == heat)
@@ -424,7 +430,9 @@ int launch_decode(const float* heat, const float* reg, const float* calib, const
     return -1;
   }
   const int n_items = ((H * W + S - 1) / S + S1_THREADS - 1) / S1_THREADS;
-  const int s1_smem = n_items * S1_THREADS * static_cast<int>(sizeof(unsigned int));
+  // score bits of the slab's pixels + the staged slab with its one-row halo
+  const int s1_smem = n_items * S1_THREADS * static_cast<int>(sizeof(unsigned int)) +
+                      ((H * W + S - 1) / S + 2 * W + 2) * static_cast<int>(sizeof(float));
   static int s1_attr = 0;
   if (s1_smem > s1_attr) {
     if (check_cuda(cudaFuncSetAttribute(nms_topk_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s1_smem),
