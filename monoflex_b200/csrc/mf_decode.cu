@@ -67,6 +67,7 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
                         ? ((static_cast<unsigned long long>(vbits[(it) * S1_THREADS]) << 15) |                                         \
                            static_cast<unsigned long long>(32767 - (lo + (it) * S1_THREADS + static_cast<int>(threadIdx.x)))) + 1ull \
                         : 0ull)
+  int my_cnt = 0;
   for (int it = 0; it < n_items; ++it) {
     const int idx = lo + it * S1_THREADS + threadIdx.x;
     unsigned int key = 0u;
@@ -89,16 +90,29 @@ nms_topk_stage1_kernel(const float* __restrict__ hm_all, int H, int W, int K, in
       key = __float_as_uint(kept);
     }
     vbits[it * S1_THREADS] = key;
-    // warp-aggregated append of the non-zero keys to the candidate list
-    const unsigned int nz = __ballot_sync(0xffffffffu, key != 0u);
-    if (nz != 0u) {
-      const int lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == __ffs(nz) - 1) base = atomicAdd(&s_ncand, __popc(nz));
-      base = __shfl_sync(0xffffffffu, base, __ffs(nz) - 1);
+    my_cnt += key != 0u ? 1 : 0;
+  }
+  // append the non-zero keys to the candidate list: ONE shared-memory atomic per warp (the per-item form issued 32 warps x 5
+  // items = 160 serialised read-modify-writes on one address), then a second pass over the thread's own score bits
+  {
+    const int lane = threadIdx.x & 31;
+    int incl = my_cnt;                                  // inclusive scan of the per-lane counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && warp_total > 0) base = atomicAdd(&s_ncand, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int slot = base + incl - my_cnt;
+    for (int it = 0; it < n_items; ++it) {
+      const unsigned int key = vbits[it * S1_THREADS];
       if (key != 0u) {
-        const int slot = base + __popc(nz & ((1u << lane) - 1u));
+        const int idx = lo + it * S1_THREADS + threadIdx.x;
         if (slot < S1_CAND) cand[slot] = ((static_cast<unsigned long long>(key) << 15) | static_cast<unsigned long long>(32767 - idx)) + 1ull;
+        ++slot;
       }
     }
   }
