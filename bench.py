@@ -692,7 +692,7 @@ def main():
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            sec, n = cpu_eval_steps(1, 1, cores, 60.0)
+            sec, n = cpu_eval_steps(6, 1, cores, 30.0)          # ~15-20 s of CPU work: a bounded sample, not the target
             cpu = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "%d full-resolution batch-1 eval forward(s) of the CPU oracle (%.1f s of CPU work each)" % (n, sec)}
         modes["strict"]["parity"] = "<= 1e-3 of the fp32 reference end to end (tests/test_gpu_model.py: 1.7e-4 .. 4.5e-4 measured)"
