@@ -405,23 +405,28 @@ def bench_train(args, rank, world, local_rank, config):
             xbufs[i % 2].copy_(host_imgs[i % n_in], non_blocking=True)
             copied[i % 2].record(copy_stream)
 
-    prev_log, last_log = None, None
+    def e2e_loop(n):
+        prev_log, last = None, None
+        prefetch(0)
+        for i in range(n):
+            main.wait_event(copied[i % 2])
+            tg = [t.to(dev) for t in host_tg[i % n_in]]
+            loss_dict, log = tr.step(xbufs[i % 2], tg, sync_log=False)
+            consumed[i % 2].record(main)               # the step's copy-in of this staging buffer is enqueued before this point
+            if i + 1 < n:
+                if i >= 1:
+                    copy_stream.wait_event(consumed[(i + 1) % 2])
+                prefetch(i + 1)
+            if prev_log is not None:
+                last = prev_log.resolve()
+            prev_log = log
+        return prev_log.resolve()
+
+    e2e_loop(2)                                        # untimed: first use of the copy stream and of the pinned log staging
     torch.cuda.synchronize()
+    copy_stream.synchronize()
     t0.record()
-    prefetch(0)
-    for i in range(args.steps):
-        main.wait_event(copied[i % 2])
-        tg = [t.to(dev) for t in host_tg[i % n_in]]
-        loss_dict, log = tr.step(xbufs[i % 2], tg, sync_log=False)
-        consumed[i % 2].record(main)                   # the step's copy-in of this staging buffer is enqueued before this point
-        if i + 1 < args.steps:
-            if i >= 1:
-                copy_stream.wait_event(consumed[(i + 1) % 2])
-            prefetch(i + 1)
-        if prev_log is not None:
-            last_log = prev_log.resolve()
-        prev_log = log
-    last_log = prev_log.resolve()
+    last_log = e2e_loop(args.steps)
     t1.record()
     torch.cuda.synchronize()
     assert all(math.isfinite(v) for v in last_log.values())
@@ -511,25 +516,30 @@ def time_inference(model, targets, host_imgs, dev_imgs, steps, B, dev, barrier):
             bufs[j].copy_(host_imgs[i % n_in], non_blocking=True)
             ready[j].record(copy_stream)
 
+    def e2e_loop(n):
+        prefetch(0)
+        prev = None
+        with torch.no_grad():
+            for i in range(n):
+                j = i % 2
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[j])
+                cur = model.forward_async(bufs[j], targets).stage()       # H2D done -> forward -> async D2H of the detections
+                done[j].record()
+                if prev is not None:                                       # read step i-1 on the host while step i runs
+                    prev.result()
+                prev = cur
+            prev.result()
+
     for j in range(2):
         done[j].record()
+    e2e_loop(3)                  # untimed: first use of the copy stream, the pinned result staging, the staging buffers
+    torch.cuda.synchronize()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    prefetch(0)
-    prev = None
-    with torch.no_grad():
-        for i in range(steps):
-            j = i % 2
-            if i + 1 < steps:
-                prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[j])
-            cur = model.forward_async(bufs[j], targets).stage()           # H2D done -> forward -> async D2H of the detections
-            done[j].record()
-            if prev is not None:                                           # read step i-1 on the host while step i runs
-                prev.result()
-            prev = cur
-        prev.result()
+    e2e_loop(steps)
     t1.record()
     torch.cuda.synchronize()
     ms_e2e = t0.elapsed_time(t1)
